@@ -1,0 +1,218 @@
+/*
+ * ldpc_b200.h -- C ABI of the B200-native LDPC sum-product (SPA) decode path.
+ *
+ * This is the drop-in boundary for the one hot path of omkuprin7/ldpc-simulator
+ * (python_ldpc_app/): SPA_Decoder.decode and the Monte-Carlo loop around it.
+ * The reference has no FFI of its own (it is pure Python), so every entry
+ * point below names the reference interface whose work it replaces
+ * (file:line relative to python_ldpc_app/).  The Python-side binding is
+ * ldpc-simulator_b200/_native.py (ctypes); INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only: pointers, sizes, ints.  No torch / CUDA types; a
+ *     CUDA stream is passed as void* (cudaStream_t), NULL = default stream.
+ *   - every function returns 0 on success or a negative ldpc_status; the
+ *     message for the calling thread is available from ldpc_last_error().
+ *     Nothing throws or longjmps across the boundary.
+ *   - "dev" pointers are device memory owned by the caller (e.g. torch
+ *     tensors); the library owns only the opaque ldpc_graph handles.
+ *   - a graph handle is immutable after creation and may be shared between
+ *     streams and threads; a workspace belongs to one in-flight call.
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with LDPC_ERR_CUDA.  The ldpc_host_* helpers are pure host
+ *     integer code (graph analysis) and need no device.
+ *
+ * Bit/LLR conventions are the reference's: LLR < 0 means bit 0,
+ * z = (posterior < 0) is the COMPLEMENT of the decided bit and is what
+ * SPA_Decoder.decode leaves in _decoded_data (spa_decoder.py:188,233,245).
+ */
+#ifndef LDPC_B200_H
+#define LDPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDPC_B200_ABI_VERSION 1
+
+typedef enum ldpc_status {
+    LDPC_OK = 0,
+    LDPC_ERR_INVALID = -1,     /* bad argument (mirrors Result.INVALID_INPUT, enums.py:6) */
+    LDPC_ERR_CUDA = -2,        /* CUDA runtime error / no device */
+    LDPC_ERR_WORKSPACE = -3,   /* workspace too small */
+    LDPC_ERR_UNSUPPORTED = -4, /* e.g. resident kernel requested for a non-QC graph */
+    LDPC_ERR_NOMEM = -5
+} ldpc_status;
+
+/* Arithmetic of the decoder. */
+typedef enum ldpc_dtype {
+    LDPC_F64 = 0,      /* parity mode: the reference's fp64 formulas literally (spa_decoder.py:133-168) */
+    LDPC_F32 = 1,      /* same formulas in fp32 with accurate tanhf/atanhf, any graph */
+    LDPC_F32_FAST = 2  /* throughput mode: SM-resident quasi-cyclic kernel, fp32 with MUFU approximations */
+} ldpc_dtype;
+
+/* Flags for ldpc_decode_batch / ldpc_mc_run. */
+#define LDPC_FLAG_EARLY_TERM    0x1u /* stop a frame at its first zero syndrome (reference behaviour,
+                                        spa_decoder.py:231-241).  Without it every frame runs exactly
+                                        max_iter passes and the syndrome is taken after the last one. */
+#define LDPC_FLAG_COMPACT       0x2u /* generic kernels: compact converged frames out of the active list */
+#define LDPC_FLAG_FIX_ODD_SIGN  0x4u /* NOT the reference: negate extrinsics of odd-degree checks, which
+                                        makes the inverted LLR convention self-consistent */
+#define LDPC_FLAG_FORCE_GENERIC 0x8u /* never pick the resident QC kernel */
+
+typedef struct ldpc_graph ldpc_graph;
+
+/* ------------------------------------------------------------------------- *
+ * Host-side graph analysis (no device needed).
+ * ------------------------------------------------------------------------- */
+
+/*
+ * Edge index of a parity-check pattern given as CSR (columns ascending within a
+ * row).  Replaces SPA_Decoder._init_neighbor_structures (spa_decoder.py:44-61)
+ * and EncoderDecoderData._init_decoder_structures (encoder_decoder_data.py:
+ * 718-747): edges are numbered in CSR order (the reference's COO order);
+ * col_ptr[n+1] / csc_edge[nnz] list, for every column, its edge numbers in
+ * ascending row order; edge_row[nnz] is the row of each edge.
+ */
+int ldpc_host_edge_index(int m, int n, const int32_t* row_ptr, const int32_t* col_idx,
+                         int32_t* col_ptr, int32_t* csc_edge, int32_t* edge_row);
+
+/*
+ * Quasi-cyclic structure detection (new; north_star item 1): finds the largest
+ * z such that H is an (m/z) x (n/z) array of z x z blocks that are each zero
+ * or a single cyclic permutation.  Returns 1 and fills z/mb/nb/shift (row-major
+ * mb*nb, -1 = zero block, else s with H[r, (r+s) mod z] = 1) when found, 0 when
+ * the matrix is not quasi-cyclic, <0 on error.  shift_cap = capacity of shift.
+ */
+int ldpc_host_detect_qc(int m, int n, const int32_t* row_ptr, const int32_t* col_idx,
+                        int* z, int* mb, int* nb, int16_t* shift, int64_t shift_cap);
+
+/*
+ * Standard form [A | I] by bit-packed GF(2) Gauss-Jordan.  Replaces
+ * gaussian_elimination + create_standart_parity_check_matrix
+ * (encoder_decoder_data.py:13-183, 269-317) with identical results: same pivot
+ * rule, same rank repair, same column permutation.
+ *   h_std_bits  [m][words] uint64, words = (n+63)/64, bit c of row r set iff
+ *               H_std[r][c] = 1 (only the first *rank rows are meaningful)
+ *   perm        [n]  H_std[:, c] = H_reduced[:, perm[c]]
+ */
+int ldpc_host_standard_form(int m, int n, const int32_t* row_ptr, const int32_t* col_idx,
+                            uint64_t* h_std_bits, int32_t* perm, int32_t* rank);
+
+/* ------------------------------------------------------------------------- *
+ * Graph handles (device resident tables).
+ * ------------------------------------------------------------------------- */
+
+/* Any parity-check pattern (raw ALIST H or the dense H_std).  Replaces
+ * SPA_Decoder.__init__ (spa_decoder.py:16-42).  Quasi-cyclic structure is
+ * detected automatically and enables LDPC_F32_FAST. */
+int ldpc_graph_create_csr(int m, int n, int64_t nnz, const int32_t* row_ptr,
+                          const int32_t* col_idx, ldpc_graph** out);
+
+/* Directly from a shift table (row-major mb*nb, -1 = zero block). */
+int ldpc_graph_create_qc(int z, int mb, int nb, const int16_t* shift, ldpc_graph** out);
+
+/* Query. Any out pointer may be NULL. */
+int ldpc_graph_info(const ldpc_graph* g, int* m, int* n, int64_t* nnz, int* max_check_degree,
+                    int* max_var_degree, int* qc_z, int* qc_mb, int* qc_nb);
+
+/* Copies the detected shift table (capacity in entries); returns 1 if QC, 0 if not. */
+int ldpc_graph_qc_shifts(const ldpc_graph* g, int16_t* shift, int64_t shift_cap);
+
+void ldpc_graph_destroy(ldpc_graph* g);
+
+/* ------------------------------------------------------------------------- *
+ * Decoding.
+ * ------------------------------------------------------------------------- */
+
+/* Bytes of workspace that let ldpc_decode_batch process `frames` frames in one
+ * chunk.  A smaller workspace is accepted (frames are then processed in
+ * several chunks) down to ldpc_workspace_bytes(g, 32, dtype). */
+size_t ldpc_workspace_bytes(const ldpc_graph* g, int64_t frames, int dtype);
+
+/*
+ * Decode `frames` frames.  Replaces SPA_Decoder.decode (spa_decoder.py:63-280),
+ * one call per batch instead of one per frame.  Asynchronous on `stream`.
+ *
+ *   llr_dev       [frames][n] row-major channel LLRs in graph-column order
+ *                 (DataBuffer._channel_data, spa_decoder.py:88); double for
+ *                 LDPC_F64, float otherwise
+ *   z_dev         [frames][n] uint8, z = (posterior < 0)   (:188,233,245)
+ *   conv_iter_dev [frames] int32, 0-based pass index at convergence, -1 = not
+ *                 converged (SPA_Decoder.convergence_iteration, :65,232)
+ *   ok_dev        [frames] uint8, 1 = Result.OK, 0 = DATA_TRANSFER_NOT_OK (:241,253)
+ *   post_dev      [frames][n] posterior LLRs of the exit pass (same type as llr)
+ *                 or NULL
+ *   norm_llr_dev  [frames] float "normalized LLR" of the exit pass
+ *                 (_d_summarize_normalized_llr, :210-228,237-251) or NULL;
+ *                 k_info = number of leading bits it is taken over (n - m)
+ */
+int ldpc_decode_batch(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
+                      const void* llr_dev, uint8_t* z_dev, int32_t* conv_iter_dev, uint8_t* ok_dev,
+                      void* post_dev, float* norm_llr_dev, int k_info,
+                      void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/*
+ * Same, with HOST buffers: the library stages chunks through pinned memory and
+ * overlaps host<->device copies with decoding on its own streams, then blocks
+ * until the results are in the host arrays.  This is the end-to-end call
+ * behind SPA_Decoder.decode / decode_batch.  z_host may be NULL when only
+ * zbits_host ([frames][4*ceil(n/32)] bytes, bit j of a frame = z[j], LSB first) is wanted.
+ */
+int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
+                           const void* llr_host, uint8_t* z_host, uint8_t* zbits_host,
+                           int32_t* conv_iter_host, uint8_t* ok_host, void* post_host,
+                           float* norm_llr_host, int k_info);
+
+/*
+ * Monte-Carlo kernel: generate `frames` BPSK-AWGN frames on the device
+ * (Philox4x32-10 + Box-Muller), decode them and fold the error counters.
+ * Replaces the per-frame loop of run_simulation / process_block
+ * (main.py:295-339, 43-146) together with Channel.process mode 1
+ * (channel.py:38-81).
+ *
+ *   speed, snr_db      sigma = 1/sqrt(2*speed*10^(snr_db/10))       (channel.py:113)
+ *   sigma_sq_quirk     1: noise stddev = sigma^2 as the reference does (channel.py:68); 0: sigma
+ *   seed, stream_id, frame_offset
+ *                      Philox key = seed; counter = (stream_id, frame_offset + frame, word) so that
+ *                      ranks / launches draw disjoint streams
+ *   codeword_dev       [n] uint8 transmitted codeword in graph-column order, NULL = all-zero
+ *   info_mask_dev      [n] uint8, 1 = information position; NULL = the first k_info positions
+ *   k_info             number of information bits; BER is taken over them (main.py:323-330)
+ *   counters_dev       uint64[5], ACCUMULATED: frames, failed frames, info-bit errors counted in
+ *                      failed frames only, sum of convergence iterations, converged frames
+ *                      (main.py:314-339)
+ */
+int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
+                double speed, double snr_db, int sigma_sq_quirk,
+                uint64_t seed, uint32_t stream_id, uint64_t frame_offset,
+                const uint8_t* codeword_dev, const uint8_t* info_mask_dev, int k_info,
+                uint64_t* counters_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Workspace for ldpc_mc_run (it also holds the generated LLRs and decoder outputs). */
+size_t ldpc_mc_workspace_bytes(const ldpc_graph* g, int64_t frames, int dtype);
+
+/* Fill llr_dev [frames][n] (float, or double when dtype == LDPC_F64) with the channel
+ * output ldpc_mc_run would decode -- used by the tests to feed identical frames to the oracle. */
+int ldpc_channel_llr(int n, int dtype, int64_t frames, double speed, double snr_db, int sigma_sq_quirk,
+                     uint64_t seed, uint32_t stream_id, uint64_t frame_offset,
+                     const uint8_t* codeword_dev, void* llr_dev, void* stream);
+
+/* Number of kernels this library launched since it was loaded (bench.py's gpu_launches). */
+uint64_t ldpc_kernel_launch_count(void);
+
+/* Saturating MUFU micro-benchmark: returns MUFU ops/s of this device in *ops_per_s
+ * (roofline denominator for the resident kernel). */
+int ldpc_measure_mufu_peak(double* ops_per_s, void* stream);
+
+const char* ldpc_last_error(void);
+int ldpc_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDPC_B200_H */

@@ -1,0 +1,99 @@
+"""ctypes binding of lib/libldpc_b200.so (C ABI: include/ldpc_b200.h).
+
+PyTorch is only the carrier of device memory and streams: every call hands the
+library raw ``tensor.data_ptr()`` values and ``torch.cuda.current_stream()``.
+There is no CPU fallback -- if the CUDA library is missing or no device is
+present the product fails loudly (``NativeLibraryError`` / ``LdpcError``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libldpc_b200.so")
+
+LDPC_F64, LDPC_F32, LDPC_F32_FAST = 0, 1, 2
+FLAG_EARLY_TERM, FLAG_COMPACT, FLAG_FIX_ODD_SIGN, FLAG_FORCE_GENERIC = 0x1, 0x2, 0x4, 0x8
+ABI_VERSION = 1
+
+EXPORTS = [
+    "ldpc_host_edge_index", "ldpc_host_detect_qc", "ldpc_host_standard_form",
+    "ldpc_graph_create_csr", "ldpc_graph_create_qc", "ldpc_graph_info", "ldpc_graph_qc_shifts",
+    "ldpc_graph_destroy", "ldpc_workspace_bytes", "ldpc_decode_batch", "ldpc_decode_batch_host",
+    "ldpc_mc_run", "ldpc_mc_workspace_bytes", "ldpc_channel_llr", "ldpc_kernel_launch_count",
+    "ldpc_measure_mufu_peak", "ldpc_last_error", "ldpc_abi_version",
+]
+
+
+class NativeLibraryError(RuntimeError):
+    """The CUDA library is not built / cannot be loaded."""
+
+
+class LdpcError(RuntimeError):
+    """A library call returned a negative ldpc_status."""
+
+    def __init__(self, code, message):
+        super().__init__(f"libldpc_b200 error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once.  Never builds implicitly and never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} is missing. Build it with `python ldpc-simulator_b200/build_native.py` "
+            "(needs nvcc). This package has no CPU fallback.")
+    try:
+        l = C.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise NativeLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    vp, i32p, i16p, u8p, u64p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int16), C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)
+    ip, i64 = C.POINTER(C.c_int), C.c_int64
+    sig = {
+        "ldpc_host_edge_index": (C.c_int, [C.c_int, C.c_int, i32p, i32p, i32p, i32p, i32p]),
+        "ldpc_host_detect_qc": (C.c_int, [C.c_int, C.c_int, i32p, i32p, ip, ip, ip, i16p, i64]),
+        "ldpc_host_standard_form": (C.c_int, [C.c_int, C.c_int, i32p, i32p, u64p, i32p, i32p]),
+        "ldpc_graph_create_csr": (C.c_int, [C.c_int, C.c_int, i64, i32p, i32p, C.POINTER(vp)]),
+        "ldpc_graph_create_qc": (C.c_int, [C.c_int, C.c_int, C.c_int, i16p, C.POINTER(vp)]),
+        "ldpc_graph_info": (C.c_int, [vp, ip, ip, C.POINTER(i64), ip, ip, ip, ip, ip]),
+        "ldpc_graph_qc_shifts": (C.c_int, [vp, i16p, i64]),
+        "ldpc_graph_destroy": (None, [vp]),
+        "ldpc_workspace_bytes": (C.c_size_t, [vp, i64, C.c_int]),
+        "ldpc_decode_batch": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_uint, vp, vp, vp, vp, vp, vp, C.c_int,
+                                        vp, C.c_size_t, vp]),
+        "ldpc_decode_batch_host": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_uint, vp, vp, vp, vp, vp, vp, vp, C.c_int]),
+        "ldpc_mc_run": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_uint, C.c_double, C.c_double, C.c_int,
+                                  C.c_uint64, C.c_uint32, C.c_uint64, vp, vp, C.c_int, vp, vp, C.c_size_t, vp]),
+        "ldpc_mc_workspace_bytes": (C.c_size_t, [vp, i64, C.c_int]),
+        "ldpc_channel_llr": (C.c_int, [C.c_int, C.c_int, i64, C.c_double, C.c_double, C.c_int, C.c_uint64,
+                                       C.c_uint32, C.c_uint64, vp, vp, vp]),
+        "ldpc_kernel_launch_count": (C.c_uint64, []),
+        "ldpc_measure_mufu_peak": (C.c_int, [C.POINTER(C.c_double), vp]),
+        "ldpc_last_error": (C.c_char_p, []),
+        "ldpc_abi_version": (C.c_int, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(l, name)
+        fn.restype = res
+        fn.argtypes = args
+    if l.ldpc_abi_version() != ABI_VERSION:
+        raise NativeLibraryError("libldpc_b200.so ABI version mismatch; rebuild it")
+    _lib = l
+    return l
+
+
+def check(rc):
+    if rc < 0:
+        raise LdpcError(rc, lib().ldpc_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def launches() -> int:
+    return int(lib().ldpc_kernel_launch_count())

@@ -1,0 +1,106 @@
+"""BPSK over AWGN -> channel LLRs (the decoder's input interface).
+
+Mirrors ``Channel.create_channel`` / ``Channel.process`` of python_ldpc_app/channel.py
+(:102-125, :38-81) for mode 1 (AWGN) and modulation 1 (BPSK), including the two
+conventions the error-rate curves depend on:
+
+* bit 0 -> symbol -1, bit 1 -> +1 (:49); LLR = 2 y / sigma^2 (:80), so LLR < 0 means bit 0;
+* the noise standard deviation is sigma**2, not sigma (:68) -- kept (``sigma_sq_quirk``).
+
+``sigma = 1/sqrt(2 * speed * 10^(snr/10))`` (:113): ``speed`` plays the role of the code rate.
+Modes 2/3 (interference) and "QPSK" are outside the decode path.
+
+B200 additions: ``process_batch`` (host, vectorised, for the parity mode with host-fed
+LLRs) and ``device_llr`` (Philox generator on the GPU, csrc/awgn_philox.cuh).
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+
+from constants import IDUM1, IDUM2
+from generator import Generator
+
+
+class Channel:
+    def __init__(self, mode, p, mod, L_c1, L_c2, L_c3):
+        self.mode, self.p, self.modulation = mode, p, mod
+        self.L_c1, self.L_c2, self.L_c3 = L_c1, L_c2, L_c3
+        self.gen_ptr = None
+        self.gen_ptr2 = None
+        self.sigma_sq_quirk = True
+        # the reference seeds from the clock (:30): runs are not reproducible unless reseeded
+        self._rng = np.random.RandomState(int(time.time() * 1e6) % (2 ** 31))
+
+    def seed(self, value):
+        self._rng = np.random.RandomState(int(value) % (2 ** 31))
+
+    def _require_awgn_bpsk(self):
+        if self.mode != 1 or self.modulation != 1:
+            raise NotImplementedError("only mode 1 (AWGN) with modulation 1 (BPSK) is on the B200 decode path")
+
+    def _noise_dev(self):
+        s = self.gen_ptr.sigma
+        return s * s if self.sigma_sq_quirk else s
+
+    def process(self, data_buffer):
+        """Append n LLRs to ``data_buffer._channel_data`` (a reused buffer grows, as in the reference)."""
+        self._require_awgn_bpsk()
+        bits = np.asarray(data_buffer._encoded_data)
+        if bits.size == 0:
+            return
+        llr = self.process_batch(bits[None, :])[0]
+        data_buffer._channel_data.extend(float(v) for v in llr)
+
+    def process_batch(self, encoded):
+        """encoded [F, n] bits -> LLRs [F, n] float64 (host)."""
+        self._require_awgn_bpsk()
+        enc = np.asarray(encoded)
+        sym = np.where(enc == 0, -1.0, 1.0)
+        noise = self._rng.normal(0.0, self._noise_dev(), size=enc.shape)
+        return 2.0 * (sym + noise) / (self.gen_ptr.sigma ** 2)
+
+    def device_llr(self, frames, n, *, seed, stream_id=0, frame_offset=0, codeword=None, dtype="f32",
+                   speed=None, snr_db=None):
+        """LLRs [frames, n] generated on the GPU by the same Philox stream ``ldpc_mc_run`` decodes."""
+        import ctypes as C
+        import torch
+        import _native
+        self._require_awgn_bpsk()
+        if speed is None or snr_db is None:
+            speed, snr_db = self._speed, self._snr_db
+        tdt = torch.float64 if dtype == "f64" else torch.float32
+        out = torch.empty((frames, n), dtype=tdt, device="cuda")
+        cw = None
+        if codeword is not None:
+            cw = torch.as_tensor(np.asarray(codeword, dtype=np.uint8)).cuda()
+        _native.check(_native.lib().ldpc_channel_llr(
+            n, _native.LDPC_F64 if dtype == "f64" else _native.LDPC_F32, frames, float(speed), float(snr_db),
+            int(self.sigma_sq_quirk), int(seed), int(stream_id), int(frame_offset),
+            cw.data_ptr() if cw is not None else None, out.data_ptr(),
+            torch.cuda.current_stream().cuda_stream))
+        return out
+
+    @staticmethod
+    def sigma_for(speed, snr_db):
+        return 1.0 / math.sqrt(2.0 * speed * (10.0 ** (snr_db * 0.1)))
+
+    @staticmethod
+    def create_channel(speed, sn1, sn2, mode, p, mod):
+        lin1, lin2 = 10.0 ** (sn1 * 0.1), 10.0 ** (sn2 * 0.1)
+        L_c1 = 4.0 * speed * lin1
+        L_c2 = 4.0 * speed / (1.0 / lin1 + 1.0 / (lin2 * p)) if p else 0.0
+        L_c3 = 4.0 * p * speed / (2.0 / lin2) + 4.0 * speed * (1.0 - p) * lin1
+        sigma1 = Channel.sigma_for(speed, sn1) if mode in (1, 2, 3) else 0.0
+        sigma2 = 0.0
+        if mode == 2 and p:
+            sigma2 = 1.0 / math.sqrt(2.0 * speed * lin2 * p)
+        elif mode == 3:
+            sigma2 = Channel.sigma_for(speed, sn2)
+        ch = Channel(mode, p, mod, L_c1, L_c2, L_c3)
+        ch.gen_ptr = Generator(IDUM1, sigma1)
+        ch.gen_ptr2 = Generator(IDUM2, sigma2)
+        ch._speed, ch._snr_db = speed, sn1
+        return ch

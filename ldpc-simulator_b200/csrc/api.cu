@@ -1,0 +1,402 @@
+// api.cu -- extern "C" entry points of include/ldpc_b200.h: argument checks,
+// kernel-path selection, the pinned-memory host pipeline and the Monte-Carlo run.
+#include "ldpc_common.cuh"
+
+#include <algorithm>
+#include <mutex>
+
+using namespace ldpc;
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+bool use_resident(const ldpc_graph* g, int dtype, unsigned flags)
+{
+    return dtype == LDPC_F32_FAST && !(flags & LDPC_FLAG_FORCE_GENERIC) && qc_resident_supported(g);
+}
+
+int check_common(const ldpc_graph* g, int dtype, int64_t frames, int max_iter)
+{
+    if (!g) { set_error("null graph"); return LDPC_ERR_INVALID; }
+    if (dtype != LDPC_F64 && dtype != LDPC_F32 && dtype != LDPC_F32_FAST) { set_error("unknown dtype %d", dtype); return LDPC_ERR_INVALID; }
+    if (frames < 0) { set_error("negative frame count"); return LDPC_ERR_INVALID; }
+    // spa_decoder.py:104,244: with max_iterations <= 0 the reference loops until the syndrome
+    // vanishes, possibly forever; refuse instead of hanging the GPU.
+    if (max_iter < 1) { set_error("max_iter must be >= 1 (got %d)", max_iter); return LDPC_ERR_INVALID; }
+    return LDPC_OK;
+}
+
+// ---- host pipeline state (grow-only, one per process) ----------------------
+struct HostSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    void* d_llr = nullptr; size_t d_llr_bytes = 0;
+    void* d_out = nullptr; size_t d_out_bytes = 0;     // z | zbits | conv | ok | post | norm
+    void* d_ws = nullptr; size_t d_ws_bytes = 0;
+    void* h_in = nullptr; size_t h_in_bytes = 0;       // pinned staging (pageable callers)
+    void* h_out = nullptr; size_t h_out_bytes = 0;
+    bool busy = false;
+};
+constexpr int kSlots = 3;
+struct HostPipe {
+    std::mutex mu;
+    HostSlot slot[kSlots];
+    bool init = false;
+};
+HostPipe g_pipe;
+
+int grow_dev(void** p, size_t* have, size_t need)
+{
+    if (*have >= need) return LDPC_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *have = 0;
+    LDPC_CUDA_TRY(cudaMalloc(p, need));
+    *have = need;
+    return LDPC_OK;
+}
+int grow_pinned(void** p, size_t* have, size_t need)
+{
+    if (*have >= need) return LDPC_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *have = 0;
+    LDPC_CUDA_TRY(cudaMallocHost(p, need));
+    *have = need;
+    return LDPC_OK;
+}
+
+bool is_pinned(const void* p)
+{
+    if (!p) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int decode_device(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
+                  const void* llr, uint8_t* z, uint32_t* zbits, int32_t* conv, uint8_t* ok, void* post,
+                  float* norm, int k_info, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+__global__ void k_pack_bits(const uint8_t* __restrict__ z, int n, int64_t frames, uint32_t* __restrict__ zbits)
+{
+    const int words = (n + 31) / 32;
+    const int64_t items = frames * words;
+    for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < items; id += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = id / words;
+        const int w = (int)(id - f * words);
+        uint32_t v = 0;
+        for (int i = 0; i < 32; ++i) {
+            const int j = w * 32 + i;
+            if (j < n && z[f * n + j]) v |= 1u << i;
+        }
+        zbits[id] = v;
+    }
+}
+
+__global__ void k_norm_zero(float* norm, int64_t frames)
+{
+    for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < frames; f += (int64_t)gridDim.x * blockDim.x) norm[f] = 0.f;
+}
+
+int decode_device(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
+                  const void* llr, uint8_t* z, uint32_t* zbits, int32_t* conv, uint8_t* ok, void* post,
+                  float* norm, int k_info, void* ws, size_t ws_bytes, cudaStream_t stream)
+{
+    if (frames == 0) return LDPC_OK;
+    if (use_resident(g, dtype, flags) && !norm) {
+        McParams mc;
+        return qc_resident_decode(g, frames, max_iter, flags, (const float*)llr, z, zbits, conv, ok,
+                                  (float*)post, mc, ws, ws_bytes, stream);
+    }
+    if (dtype == LDPC_F32_FAST && !(flags & LDPC_FLAG_FORCE_GENERIC) && !norm && !qc_resident_supported(g)) {
+        set_error("LDPC_F32_FAST needs a quasi-cyclic graph supported by the resident kernel; "
+                  "use LDPC_F32 (or LDPC_FLAG_FORCE_GENERIC) for this graph");
+        return LDPC_ERR_UNSUPPORTED;
+    }
+    if (!z) { set_error("the generic path needs z_dev"); return LDPC_ERR_INVALID; }
+    int rc = generic_decode(g, dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32, frames, max_iter, flags, llr, z, conv, ok,
+                            post, norm, k_info, ws, ws_bytes, stream);
+    if (rc) return rc;
+    if (zbits) {
+        DeviceInfo di;
+        rc = get_device_info(&di);
+        if (rc) return rc;
+        const int64_t items = frames * ((g->n + 31) / 32);
+        k_pack_bits<<<(int)std::min<int64_t>((items + 255) / 256, (int64_t)di.sm_count * 8), 256, 0, stream>>>(z, g->n, frames, zbits);
+        LDPC_LAUNCH_CHECK();
+    }
+    return LDPC_OK;
+}
+
+// Saturating MUFU kernel: 8 independent ex2 chains per thread.
+__global__ void __launch_bounds__(256) k_mufu_peak(float* sink, int iters)
+{
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = -1.0f - 0.001f * (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float y;
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a[i]));
+            a[i] = y - 1.5f;      // keeps the argument in (-1.5, -0.5): one FADD per MUFU
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == 123456.f) sink[0] = s;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+extern "C" size_t ldpc_workspace_bytes(const ldpc_graph* g, int64_t frames, int dtype)
+{
+    if (!g || frames < 0) return 0;
+    if (dtype == LDPC_F32_FAST && qc_resident_supported(g)) return 256;
+    return generic_workspace_bytes(g, std::max<int64_t>(frames, 1), dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32);
+}
+
+extern "C" int ldpc_decode_batch(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
+                                 const void* llr_dev, uint8_t* z_dev, int32_t* conv_iter_dev, uint8_t* ok_dev,
+                                 void* post_dev, float* norm_llr_dev, int k_info,
+                                 void* workspace_dev, size_t workspace_bytes, void* stream)
+{
+    int rc = check_common(g, dtype, frames, max_iter);
+    if (rc) return rc;
+    if (frames == 0) return LDPC_OK;
+    if (!llr_dev || !z_dev || !conv_iter_dev || !ok_dev) { set_error("null device buffer"); return LDPC_ERR_INVALID; }
+    if (norm_llr_dev && (k_info < 0 || k_info > g->n)) { set_error("k_info out of range"); return LDPC_ERR_INVALID; }
+    return decode_device(g, dtype, frames, max_iter, flags, llr_dev, z_dev, nullptr, conv_iter_dev, ok_dev,
+                         post_dev, norm_llr_dev, k_info, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
+                                      const void* llr_host, uint8_t* z_host, uint8_t* zbits_host,
+                                      int32_t* conv_iter_host, uint8_t* ok_host, void* post_host,
+                                      float* norm_llr_host, int k_info)
+{
+    int rc = check_common(g, dtype, frames, max_iter);
+    if (rc) return rc;
+    if (frames == 0) return LDPC_OK;
+    if (!llr_host || !conv_iter_host || !ok_host || (!z_host && !zbits_host)) { set_error("null host buffer"); return LDPC_ERR_INVALID; }
+    if (norm_llr_host && (k_info < 0 || k_info > g->n)) { set_error("k_info out of range"); return LDPC_ERR_INVALID; }
+    DeviceInfo di;
+    rc = get_device_info(&di);
+    if (rc) return rc;
+
+    const int n = g->n;
+    const size_t esz = dtype == LDPC_F64 ? 8 : 4;
+    const int words = (n + 31) / 32;
+    const bool resident = use_resident(g, dtype, flags) && !norm_llr_host;
+    const bool need_z_dev = z_host || !resident;       // generic kernels always produce bytes
+    // chunk size: ~64 MB of LLRs per slot for the resident path, bounded workspace for the generic one
+    int64_t chunk = std::max<int64_t>(32, ((int64_t)64 << 20) / (int64_t)(n * esz));
+    if (!resident) {
+        const size_t per32 = generic_workspace_bytes(g, 32, dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32);
+        const int64_t by_ws = std::max<int64_t>(32, (int64_t)(((size_t)3 << 30) / per32) * 32);
+        chunk = std::min(chunk, by_ws);
+    }
+    chunk = std::min<int64_t>((chunk + 31) / 32 * 32, (frames + 31) / 32 * 32);
+
+    // output block layout inside one slot (all 256-byte aligned)
+    size_t o_z = 0, o_zb, o_conv, o_ok, o_post, o_norm, o_end;
+    o_zb = o_z + (need_z_dev ? align_up((size_t)chunk * n, 256) : 0);
+    o_conv = o_zb + (zbits_host ? align_up((size_t)chunk * words * 4, 256) : 0);
+    o_ok = o_conv + align_up((size_t)chunk * 4, 256);
+    o_post = o_ok + align_up((size_t)chunk, 256);
+    o_norm = o_post + (post_host ? align_up((size_t)chunk * n * esz, 256) : 0);
+    o_end = o_norm + (norm_llr_host ? align_up((size_t)chunk * 4, 256) : 0);
+    const size_t ws_need = resident ? 256 : generic_workspace_bytes(g, chunk, dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32);
+
+    const bool in_pinned = is_pinned(llr_host);
+    const bool out_pinned = is_pinned(z_host) && is_pinned(zbits_host) && is_pinned(conv_iter_host) &&
+                            is_pinned(ok_host) && is_pinned(post_host) && is_pinned(norm_llr_host);
+
+    std::lock_guard<std::mutex> lk(g_pipe.mu);
+    if (!g_pipe.init) {
+        for (int s = 0; s < kSlots; ++s) {
+            LDPC_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.slot[s].stream, cudaStreamNonBlocking));
+            LDPC_CUDA_TRY(cudaEventCreateWithFlags(&g_pipe.slot[s].done, cudaEventDisableTiming));
+        }
+        g_pipe.init = true;
+    }
+    const int nslots = (int)std::min<int64_t>(kSlots, (frames + chunk - 1) / chunk);
+    for (int s = 0; s < nslots; ++s) {
+        HostSlot& sl = g_pipe.slot[s];
+        if ((rc = grow_dev(&sl.d_llr, &sl.d_llr_bytes, (size_t)chunk * n * esz))) return rc;
+        if ((rc = grow_dev(&sl.d_out, &sl.d_out_bytes, o_end))) return rc;
+        if ((rc = grow_dev(&sl.d_ws, &sl.d_ws_bytes, ws_need))) return rc;
+        if (!in_pinned && (rc = grow_pinned(&sl.h_in, &sl.h_in_bytes, (size_t)chunk * n * esz))) return rc;
+        if (!out_pinned && (rc = grow_pinned(&sl.h_out, &sl.h_out_bytes, o_end))) return rc;
+        sl.busy = false;
+    }
+
+    struct Pending { int64_t f0 = 0, cnt = 0; };
+    Pending pend[kSlots];
+    auto drain = [&](int s) -> int {      // wait for a slot and copy staged outputs to the caller
+        HostSlot& sl = g_pipe.slot[s];
+        if (!sl.busy) return LDPC_OK;
+        LDPC_CUDA_TRY(cudaEventSynchronize(sl.done));
+        sl.busy = false;
+        if (!out_pinned) {
+            const int64_t f0 = pend[s].f0, c = pend[s].cnt;
+            const char* h = (const char*)sl.h_out;
+            if (z_host) memcpy(z_host + (size_t)f0 * n, h + o_z, (size_t)c * n);
+            if (zbits_host) memcpy(zbits_host + (size_t)f0 * words * 4, h + o_zb, (size_t)c * words * 4);
+            memcpy(conv_iter_host + f0, h + o_conv, (size_t)c * 4);
+            memcpy(ok_host + f0, h + o_ok, (size_t)c);
+            if (post_host) memcpy((char*)post_host + (size_t)f0 * n * esz, h + o_post, (size_t)c * n * esz);
+            if (norm_llr_host) memcpy(norm_llr_host + f0, h + o_norm, (size_t)c * 4);
+        }
+        return LDPC_OK;
+    };
+
+    int s = 0;
+    for (int64_t f0 = 0; f0 < frames; f0 += chunk, s = (s + 1) % nslots) {
+        if ((rc = drain(s))) return rc;
+        HostSlot& sl = g_pipe.slot[s];
+        const int64_t c = std::min<int64_t>(chunk, frames - f0);
+        const char* src = (const char*)llr_host + (size_t)f0 * n * esz;
+        const size_t in_bytes = (size_t)c * n * esz;
+        if (!in_pinned) { memcpy(sl.h_in, src, in_bytes); src = (const char*)sl.h_in; }
+        LDPC_CUDA_TRY(cudaMemcpyAsync(sl.d_llr, src, in_bytes, cudaMemcpyHostToDevice, sl.stream));
+        char* d = (char*)sl.d_out;
+        rc = decode_device(g, dtype, c, max_iter, flags, sl.d_llr, need_z_dev ? (uint8_t*)(d + o_z) : nullptr,
+                           zbits_host ? (uint32_t*)(d + o_zb) : nullptr, (int32_t*)(d + o_conv), (uint8_t*)(d + o_ok),
+                           post_host ? (void*)(d + o_post) : nullptr, norm_llr_host ? (float*)(d + o_norm) : nullptr,
+                           k_info, sl.d_ws, sl.d_ws_bytes, sl.stream);
+        if (rc) return rc;
+        auto d2h = [&](void* user, size_t user_off, size_t slot_off, size_t bytes) -> int {
+            void* dst = out_pinned ? (void*)((char*)user + user_off) : (void*)((char*)sl.h_out + slot_off);
+            LDPC_CUDA_TRY(cudaMemcpyAsync(dst, d + slot_off, bytes, cudaMemcpyDeviceToHost, sl.stream));
+            return LDPC_OK;
+        };
+        if (z_host && (rc = d2h(z_host, (size_t)f0 * n, o_z, (size_t)c * n))) return rc;
+        if (zbits_host && (rc = d2h(zbits_host, (size_t)f0 * words * 4, o_zb, (size_t)c * words * 4))) return rc;
+        if ((rc = d2h(conv_iter_host, (size_t)f0 * 4, o_conv, (size_t)c * 4))) return rc;
+        if ((rc = d2h(ok_host, (size_t)f0, o_ok, (size_t)c))) return rc;
+        if (post_host && (rc = d2h(post_host, (size_t)f0 * n * esz, o_post, (size_t)c * n * esz))) return rc;
+        if (norm_llr_host && (rc = d2h(norm_llr_host, (size_t)f0 * 4, o_norm, (size_t)c * 4))) return rc;
+        LDPC_CUDA_TRY(cudaEventRecord(sl.done, sl.stream));
+        sl.busy = true;
+        pend[s].f0 = f0; pend[s].cnt = c;
+    }
+    for (int q = 0; q < nslots; ++q)
+        if ((rc = drain(q))) return rc;
+    return LDPC_OK;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" size_t ldpc_mc_workspace_bytes(const ldpc_graph* g, int64_t frames, int dtype)
+{
+    if (!g || frames < 0) return 0;
+    if (dtype == LDPC_F32_FAST && qc_resident_supported(g)) return 256;
+    const size_t esz = dtype == LDPC_F64 ? 8 : 4;
+    const int64_t F = std::max<int64_t>(frames, 1);
+    return align_up((size_t)F * g->n * esz, 256) + align_up((size_t)F * g->n, 256) + align_up((size_t)F * 4, 256) +
+           align_up((size_t)F, 256) + generic_workspace_bytes(g, F, dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32);
+}
+
+extern "C" int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
+                           double speed, double snr_db, int sigma_sq_quirk,
+                           uint64_t seed, uint32_t stream_id, uint64_t frame_offset,
+                           const uint8_t* codeword_dev, const uint8_t* info_mask_dev, int k_info,
+                           uint64_t* counters_dev, void* workspace_dev, size_t workspace_bytes, void* stream_v)
+{
+    int rc = check_common(g, dtype, frames, max_iter);
+    if (rc) return rc;
+    if (!counters_dev) { set_error("null counters"); return LDPC_ERR_INVALID; }
+    if (!(speed > 0.0)) { set_error("speed must be positive"); return LDPC_ERR_INVALID; }
+    if (k_info < 0 || k_info > g->n) { set_error("k_info out of range"); return LDPC_ERR_INVALID; }
+    if (frames == 0) return LDPC_OK;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    if (use_resident(g, dtype, flags)) {
+        McParams mc;
+        mc.active = true;
+        channel_params(speed, snr_db, sigma_sq_quirk, seed, stream_id, &mc);
+        mc.frame_offset = frame_offset;
+        mc.codeword = codeword_dev;
+        mc.info_mask = info_mask_dev;
+        mc.k_info = k_info;
+        mc.counters = (unsigned long long*)counters_dev;
+        return qc_resident_decode(g, frames, max_iter, flags, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                  mc, workspace_dev, workspace_bytes, stream);
+    }
+    if (dtype == LDPC_F32_FAST && !(flags & LDPC_FLAG_FORCE_GENERIC)) {
+        set_error("LDPC_F32_FAST needs a quasi-cyclic graph supported by the resident kernel");
+        return LDPC_ERR_UNSUPPORTED;
+    }
+    // generic path: generate -> decode -> count, chunked to the workspace
+    const int gd = dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32;
+    const size_t esz = gd == LDPC_F64 ? 8 : 4;
+    const int n = g->n;
+    auto need = [&](int64_t F) {
+        return align_up((size_t)F * n * esz, 256) + align_up((size_t)F * n, 256) + align_up((size_t)F * 4, 256) +
+               align_up((size_t)F, 256) + generic_workspace_bytes(g, F, gd);
+    };
+    int64_t chunk = (frames + 31) / 32 * 32;
+    while (chunk > 32 && need(chunk) > workspace_bytes) chunk = std::max<int64_t>(32, (chunk / 2 + 31) / 32 * 32);
+    if (!workspace_dev || need(chunk) > workspace_bytes) {
+        set_error("Monte-Carlo workspace of %zu bytes is too small (%zu for 32 frames)", workspace_bytes, need(32));
+        return LDPC_ERR_WORKSPACE;
+    }
+    char* p = (char*)workspace_dev;
+    void* llr = p; p += align_up((size_t)chunk * n * esz, 256);
+    uint8_t* z = (uint8_t*)p; p += align_up((size_t)chunk * n, 256);
+    int32_t* conv = (int32_t*)p; p += align_up((size_t)chunk * 4, 256);
+    uint8_t* ok = (uint8_t*)p; p += align_up((size_t)chunk, 256);
+    const size_t ws_bytes = workspace_bytes - (size_t)(p - (char*)workspace_dev);
+    for (int64_t f0 = 0; f0 < frames; f0 += chunk) {
+        const int64_t c = std::min<int64_t>(chunk, frames - f0);
+        rc = channel_fill(n, gd, c, speed, snr_db, sigma_sq_quirk, seed, stream_id, frame_offset + (uint64_t)f0,
+                          codeword_dev, llr, stream);
+        if (rc) return rc;
+        rc = generic_decode(g, gd, c, max_iter, flags, llr, z, conv, ok, nullptr, nullptr, 0, p, ws_bytes, stream);
+        if (rc) return rc;
+        rc = count_errors(n, k_info, c, z, ok, conv, codeword_dev, info_mask_dev, (unsigned long long*)counters_dev, stream);
+        if (rc) return rc;
+    }
+    return LDPC_OK;
+}
+
+extern "C" int ldpc_channel_llr(int n, int dtype, int64_t frames, double speed, double snr_db, int sigma_sq_quirk,
+                                uint64_t seed, uint32_t stream_id, uint64_t frame_offset,
+                                const uint8_t* codeword_dev, void* llr_dev, void* stream)
+{
+    return channel_fill(n, dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32, frames, speed, snr_db, sigma_sq_quirk, seed,
+                        stream_id, frame_offset, codeword_dev, llr_dev, (cudaStream_t)stream);
+}
+
+extern "C" int ldpc_measure_mufu_peak(double* ops_per_s, void* stream_v)
+{
+    if (!ops_per_s) { set_error("null output"); return LDPC_ERR_INVALID; }
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    float* sink = nullptr;
+    LDPC_CUDA_TRY(cudaMalloc(&sink, 4));
+    cudaEvent_t e0, e1;
+    LDPC_CUDA_TRY(cudaEventCreate(&e0));
+    LDPC_CUDA_TRY(cudaEventCreate(&e1));
+    const int iters = 4096, grid = di.sm_count * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        LDPC_CUDA_TRY(cudaEventRecord(e0, stream));
+        k_mufu_peak<<<grid, 256, 0, stream>>>(sink, iters);
+        LDPC_LAUNCH_CHECK();
+        LDPC_CUDA_TRY(cudaEventRecord(e1, stream));
+        LDPC_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        LDPC_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double ops = (double)grid * 256.0 * 8.0 * iters;
+        if (rep > 0 && ms > 0.f) best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *ops_per_s = best;
+    return LDPC_OK;
+}

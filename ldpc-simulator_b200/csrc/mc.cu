@@ -1,0 +1,142 @@
+// mc.cu -- device-side channel fill and error-counter fold for the Monte-Carlo path.
+//
+// Replaces the per-frame bookkeeping of run_simulation / process_block
+// (python_ldpc_app/main.py:295-339, 43-146): frame error = final syndrome != 0;
+// info-bit errors are counted ONLY in failed frames, on the un-complemented
+// decoder output (main.py:323-330); the convergence iteration is summed over
+// converged frames (:336-339).
+#include "ldpc_common.cuh"
+#include "awgn_philox.cuh"
+
+#include <cmath>
+
+namespace ldpc {
+
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_channel_fill(int n, int64_t frames, ChannelConst cc, uint64_t frame_offset,
+               const uint8_t* __restrict__ codeword, T* __restrict__ llr)
+{
+    const int quads = (n + 3) / 4;
+    const int64_t items = frames * quads;
+    for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < items;
+         id += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = id / quads;
+        const uint32_t q = (uint32_t)(id - f * quads);
+        uint32_t bits = 0;
+        if (codeword) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if ((int)(4 * q + i) < n && codeword[4 * q + i]) bits |= 1u << i;
+        }
+        float v[4];
+        channel_llr4(cc, frame_offset + (uint64_t)f, q, bits, v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if ((int)(4 * q + i) < n) llr[f * n + 4 * q + i] = (T)v[i];
+    }
+}
+
+// One warp per frame.
+__global__ void __launch_bounds__(256)
+k_count_errors(int n, int k_info, int64_t frames, const uint8_t* __restrict__ z,
+               const uint8_t* __restrict__ ok, const int32_t* __restrict__ conv,
+               const uint8_t* __restrict__ codeword, const uint8_t* __restrict__ info_mask,
+               unsigned long long* __restrict__ counters)
+{
+    __shared__ unsigned long long acc[5];
+    if (threadIdx.x < 5) acc[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long c_fr = 0, c_fe = 0, c_be = 0, c_cs = 0, c_cc = 0;
+    for (int64_t f = warp0; f < frames; f += nwarps) {
+        const bool good = ok[f] != 0;
+        if (!good) {                                                     // main.py:326
+            int errs = 0;
+            const int span = info_mask ? n : k_info;
+            for (int j = lane; j < span; j += 32) {
+                if (info_mask && !info_mask[j]) continue;
+                const unsigned est = z[f * n + j] ^ 1u;                  // :328
+                const unsigned sent = codeword ? codeword[j] : 0u;
+                errs += (est != sent);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) errs += __shfl_xor_sync(0xffffffffu, errs, o);
+            if (lane == 0) { c_be += (unsigned)errs; c_fe += 1; }
+        }
+        if (lane == 0) {
+            c_fr += 1;
+            const int ci = conv[f];
+            if (ci >= 0) { c_cs += (unsigned)ci; c_cc += 1; }            // :336-339
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&acc[0], c_fr); atomicAdd(&acc[1], c_fe); atomicAdd(&acc[2], c_be);
+        atomicAdd(&acc[3], c_cs); atomicAdd(&acc[4], c_cc);
+    }
+    __syncthreads();
+    if (threadIdx.x < 5 && acc[threadIdx.x]) atomicAdd(&counters[threadIdx.x], acc[threadIdx.x]);
+}
+
+}  // namespace
+
+static ChannelConst make_channel_const(double speed, double snr_db, int quirk, uint64_t seed, uint32_t stream_id)
+{
+    const double sigma = 1.0 / std::sqrt(2.0 * speed * std::pow(10.0, snr_db * 0.1));   // channel.py:113
+    ChannelConst cc;
+    cc.noise_dev = (float)(quirk ? sigma * sigma : sigma);                              // channel.py:68
+    cc.llr_scale = (float)(2.0 / (sigma * sigma));                                      // channel.py:80
+    cc.k0 = (uint32_t)seed;
+    cc.k1 = (uint32_t)(seed >> 32);
+    cc.stream_id = stream_id;
+    return cc;
+}
+
+int channel_fill(int n, int dtype, int64_t frames, double speed, double snr_db, int quirk, uint64_t seed,
+                 uint32_t stream_id, uint64_t frame_offset, const uint8_t* codeword_dev, void* llr_dev,
+                 cudaStream_t stream)
+{
+    if (n <= 0 || frames < 0 || !llr_dev || !(speed > 0.0)) { set_error("bad channel arguments"); return LDPC_ERR_INVALID; }
+    if (frames == 0) return LDPC_OK;
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc) return rc;
+    const ChannelConst cc = make_channel_const(speed, snr_db, quirk, seed, stream_id);
+    const int64_t items = frames * ((n + 3) / 4);
+    const int grid = (int)std::min<int64_t>((items + 255) / 256, (int64_t)di.sm_count * 16);
+    if (dtype == LDPC_F64)
+        k_channel_fill<double><<<grid, 256, 0, stream>>>(n, frames, cc, frame_offset, codeword_dev, (double*)llr_dev);
+    else
+        k_channel_fill<float><<<grid, 256, 0, stream>>>(n, frames, cc, frame_offset, codeword_dev, (float*)llr_dev);
+    LDPC_LAUNCH_CHECK();
+    return LDPC_OK;
+}
+
+void channel_params(double speed, double snr_db, int quirk, uint64_t seed, uint32_t stream_id, McParams* mc)
+{
+    const ChannelConst cc = make_channel_const(speed, snr_db, quirk, seed, stream_id);
+    mc->noise_dev = cc.noise_dev;
+    mc->llr_scale = cc.llr_scale;
+    mc->seed = seed;
+    mc->stream_id = stream_id;
+}
+
+int count_errors(int n, int k_info, int64_t frames, const uint8_t* z_dev, const uint8_t* ok_dev,
+                 const int32_t* conv_dev, const uint8_t* codeword_dev, const uint8_t* info_mask_dev,
+                 unsigned long long* counters_dev, cudaStream_t stream)
+{
+    if (frames == 0) return LDPC_OK;
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc) return rc;
+    const int grid = (int)std::min<int64_t>((frames * 32 + 255) / 256, (int64_t)di.sm_count * 8);
+    k_count_errors<<<grid, 256, 0, stream>>>(n, k_info, frames, z_dev, ok_dev, conv_dev, codeword_dev, info_mask_dev, counters_dev);
+    LDPC_LAUNCH_CHECK();
+    return LDPC_OK;
+}
+
+}  // namespace ldpc
