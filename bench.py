@@ -116,7 +116,7 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     from oracle import spa_oracle as so
     so.build()
-    per_step = 24 * cores
+    per_step = 192 * cores
     for _ in range(args.warmup):
         cpu_reference_run(max(cores, per_step // 8), cores)
     t_total, bits = 0.0, 0.0
@@ -293,7 +293,7 @@ def main():
     cores = os.cpu_count() or 1
     cpu = None
     if world == 1:
-        sample = args.cpu_frames or 32 * cores
+        sample = args.cpu_frames or 2048 * cores
         rate, secs = cpu_reference_run(sample, cores)
         cpu = {"value": rate / 1e9, "unit": "Gbit/s", "cores": cores, "kind": "port",
                "sample": f"{sample} frames of the same workload in {secs:.1f} s, oracle/spa_oracle.c "
