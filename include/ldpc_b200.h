@@ -63,6 +63,8 @@ typedef enum ldpc_dtype {
 #define LDPC_FLAG_FIX_ODD_SIGN  0x4u /* NOT the reference: negate extrinsics of odd-degree checks, which
                                         makes the inverted LLR convention self-consistent */
 #define LDPC_FLAG_FORCE_GENERIC 0x8u /* never pick the resident QC kernel */
+#define LDPC_FLAG_TABLE_KERNEL  0x10u /* resident path: use the table-driven kernel even when a kernel
+                                         specialised at build time for this base matrix exists (tests) */
 
 typedef struct ldpc_graph ldpc_graph;
 

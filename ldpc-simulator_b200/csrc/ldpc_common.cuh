@@ -104,6 +104,11 @@ int qc_resident_decode(const ldpc_graph* g, int64_t frames, int max_iter, unsign
                        uint8_t* ok_dev, float* post_dev, const McParams& mc, void* ws, size_t ws_bytes,
                        cudaStream_t stream);
 void qc_resident_release(ldpc_graph* g);
+// compile-time specialised kernels for registered base matrices, spa_qc_spec.cu
+int qc_spec_find(const ldpc_graph* g);   // registry index or -1
+int qc_spec_decode(int idx, const ldpc_graph* g, int64_t frames, int max_iter, unsigned flags,
+                   const float* llr_dev, uint8_t* z_dev, uint32_t* zbits_dev, int32_t* conv_dev,
+                   uint8_t* ok_dev, float* post_dev, const McParams& mc, void* ws, cudaStream_t stream);
 
 // ---- channel / counters, mc.cu ---------------------------------------------
 int channel_fill(int n, int dtype, int64_t frames, double speed, double snr_db, int quirk, uint64_t seed,

@@ -421,6 +421,12 @@ int qc_resident_decode(const ldpc_graph* g, int64_t frames, int max_iter, unsign
     if (!qc_resident_supported(g)) { set_error("graph is not supported by the resident QC kernel"); return LDPC_ERR_UNSUPPORTED; }
     if (frames == 0) return LDPC_OK;
     if (ws && ws_bytes < 256) ws = nullptr;
+    if (!(flags & LDPC_FLAG_TABLE_KERNEL)) {
+        const int spec = qc_spec_find(g);
+        if (spec >= 0)
+            return qc_spec_decode(spec, g, frames, max_iter, flags, llr_dev, z_dev, zbits_dev, conv_dev, ok_dev,
+                                  post_dev, mc, ws, stream);
+    }
     Outputs out{z_dev, zbits_dev, conv_dev, ok_dev, post_dev};
     switch (pick_shape(g)) {
         case 0: return launch_shape<12, 7>(g, frames, max_iter, flags, llr_dev, out, mc, ws, stream);
