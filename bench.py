@@ -145,7 +145,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=131072, help="frames per step per GPU")
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
@@ -216,6 +216,10 @@ def main():
     # ---- device-resident timing -------------------------------------------------------------------
     for _ in range(args.warmup):
         step_device()
+    t_spin = time.perf_counter()             # let the clocks settle: keep the GPU busy for >= 0.5 s before timing
+    while time.perf_counter() - t_spin < 0.5:
+        step_device()
+        torch.cuda.synchronize()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:

@@ -11,14 +11,14 @@ namespace ldpc {
 
 namespace {
 
-template <class C, bool EARLY, int THREADS, int MINB>
+template <class C, bool EARLY, int THREADS, int MINB, bool SPLIT = false>
 int launch_spec(C code, const ldpc_graph* g, int64_t frames, int max_iter, unsigned flags, const float* llr,
                 const qc::Outputs& out, const McParams& mc, void* ws, cudaStream_t stream)
 {
     DeviceInfo di;
     int rc = get_device_info(&di);
     if (rc) return rc;
-    auto kp = qc::k_qc_spec<THREADS, MINB, EARLY, C>;
+    auto kp = qc::k_qc_spec<THREADS, MINB, EARLY, SPLIT, C>;
     const size_t smem = sizeof(float) * 3 * (size_t)C::N;
     static thread_local bool configured = false;
     static thread_local int per_sm = 0;
@@ -52,19 +52,28 @@ template <class C>
 int launch_code(C code, const Args& a)
 {
     const bool early = (a.flags & LDPC_FLAG_EARLY_TERM) != 0;
-    constexpr int T = C::Z <= 32 ? 32 : (C::Z <= 64 ? 64 : (C::Z <= 96 ? 96 : 128));
-    // resident CTAs per SM the register budget is sized for (65536 regs / (T * regs))
-    constexpr int B = T == 32 ? 16 : (T == 64 ? 8 : (T == 96 ? 5 : 4));
+    constexpr int TZ = (C::Z + 31) / 32 * 32;
+    constexpr int T = TZ * C::TEAMS;                 // CTA = teams x ceil32(z) threads
+    // CTAs per SM the register budget is sized for.  Measured on B200 (profiles/r1_tuning.md): the
+    // kernel is bound by instruction issue and the MUFU pipe, not by latency, so a spill-free build
+    // with 12 warps per SM beats a 24-warp build that spills; 168 registers per thread hold the
+    // messages, the hoisted rotated addresses and the working set of one check row.
+    constexpr int NEED = 2 * C::MAXSLOT + 60;
+    constexpr int B0 = 65536 / (T * (NEED > 168 ? 255 : 168));
+    constexpr int B = B0 < 1 ? 1 : (B0 > 32 ? 32 : B0);
 #define LDPC_GO(BB)                                                                                                  \
     return early ? launch_spec<C, true, T, BB>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream) \
                  : launch_spec<C, false, T, BB>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream)
 #ifdef LDPC_QC_TUNING
     // tuning builds only: LDPC_QC_MINB selects the occupancy target of the 96-thread kernels
-    if (T == 96) {
+    if (T == 192) {
         const char* e = getenv("LDPC_QC_MINB");
         const int want = e ? atoi(e) : B;
-        if (want == 4) { LDPC_GO(4); }
-        if (want == 6) { LDPC_GO(6); }
+        const bool split = getenv("LDPC_QC_SPLIT") && atoi(getenv("LDPC_QC_SPLIT"));
+#define LDPC_GO2(BB) do { if (split) { return early ? launch_spec<C, true, T, BB, true>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream) : launch_spec<C, false, T, BB, true>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream); } } while (0)
+        if (want == 2) { LDPC_GO2(2); LDPC_GO(2); }
+        if (want == 3) { LDPC_GO2(3); LDPC_GO(3); }
+        if (want == 4) { LDPC_GO2(4); LDPC_GO(4); }
     }
 #endif
     LDPC_GO(B);

@@ -107,19 +107,22 @@ class SPA_Decoder:
             raise ValueError(f"unknown precision {name!r}")
         return name, _PRECISIONS[name]
 
-    def _flags(self, early_termination=None, compact=False):
+    def _flags(self, early_termination=None, compact=False, table_kernel=False):
         s = self.m_pSettings
         early = getattr(s, "is_early_termination", lambda: True)() if early_termination is None else early_termination
         flags = _native.FLAG_EARLY_TERM if early else 0
         if compact:
             flags |= _native.FLAG_COMPACT
+        if table_kernel:
+            flags |= _native.FLAG_TABLE_KERNEL
         if getattr(s, "is_fix_odd_check_sign", lambda: False)():
             flags |= _native.FLAG_FIX_ODD_SIGN
         return flags
 
     # ---- batched decode, host buffers (the end-to-end call) -------------------------
     def decode_batch(self, llr, *, precision=None, early_termination=None, compact=False, want_z=True,
-                     want_bits=False, want_posterior=False, normalized_llr=None, max_iterations=None):
+                     want_bits=False, want_posterior=False, normalized_llr=None, max_iterations=None,
+                     table_kernel=False):
         """Decode F frames given as a host array ``llr`` [F, n] (numpy, or a pinned CPU torch tensor).
 
         Returns a ``BatchResult`` of host numpy arrays.  Host<->device copies are pipelined inside
@@ -160,7 +163,7 @@ class SPA_Decoder:
         k_info = int(self.m_pData._n - self.m_pData._m) if calc_norm else 0
         ptr = lambda a: a.ctypes.data if a is not None else None
         _native.check(_native.lib().ldpc_decode_batch_host(
-            g.handle, dtype, frames, int(max_it), self._flags(early_termination, compact), in_ptr,
+            g.handle, dtype, frames, int(max_it), self._flags(early_termination, compact, table_kernel), in_ptr,
             ptr(z), ptr(zbits), ptr(conv), ptr(ok), ptr(post), ptr(norm), k_info))
         del keep
         return BatchResult(z, zbits, ok, conv, post, norm)

@@ -195,6 +195,44 @@ def test_resident_kernel_equals_generic_fp32_semantics_on_converging_frames():
     assert (fast.ok == gen.ok).mean() > 0.99
 
 
+@pytest.mark.parametrize("name", ["wimax_576_0.5", "wimax_2304_0.5", "wimax_2304_0.75B", "wifi_648_r083", "tanner_155_64"])
+def test_specialised_and_table_driven_resident_kernels_agree(name):
+    """Codes listed in csrc/qc_registry.json run a kernel specialised at build time; every other
+    quasi-cyclic code (here wifi-648 z=27, Tanner z=31) runs the table-driven kernel.  Same arithmetic:
+    identical decisions, posteriors equal to fp32 rounding (the row order inside a pass differs)."""
+    code = load_code(name)
+    rng = np.random.default_rng(17)
+    llr = awgn_llr(rng, 384, code.n, np.resize(np.array([2.0, 4.0, 6.0]), 384)).astype(np.float32)
+    ref = oracle(code, llr.astype(np.float64), 12)
+    for early in (True, False):
+        tab = make_decoder(code, 12, "f32_fast").decode_batch(llr, want_posterior=True, table_kernel=True,
+                                                               early_termination=early)
+        spec = make_decoder(code, 12, "f32_fast").decode_batch(llr, want_posterior=True, early_termination=early)
+        assert (tab.z == spec.z).mean() > 0.9999 and (tab.conv_it == spec.conv_it).mean() > 0.99
+        np.testing.assert_allclose(spec.post, tab.post, rtol=2e-3, atol=2e-3)
+        if early:
+            assert (tab.z == ref["z"]).mean() > 0.999 and (tab.ok == ref["ok"]).mean() > 0.98
+
+
+def test_early_termination_on_the_largest_code_matches_fixed_schedule():
+    """Config 3: wimax_2304_0.75B (E = 8448, check degree 14/15) at an Eb/N0 where part of the batch
+    converges early.  Frames leave the active set as soon as their syndrome vanishes (dynamic frame
+    queue in the resident kernel, active-list compaction in the generic kernels); per-frame results
+    must equal those of the reference schedule."""
+    code = load_code("wimax_2304_0.75B")
+    rng = np.random.default_rng(33)
+    llr = awgn_llr(rng, 1024, code.n, np.resize(np.array([3.0, 3.5, 4.0, 4.5]), 1024), rate=0.75)
+    ref = oracle(code, llr, 20)
+    assert 0.05 < ref["ok"].mean() < 0.999
+    g64 = make_decoder(code, 20, "f64").decode_batch(llr, compact=True, want_posterior=True)
+    assert not frame_mismatch(g64, ref).any()
+    assert not posterior_violations(g64.post, ref["post"]).any()
+    fast = make_decoder(code, 20, "f32_fast").decode_batch(llr.astype(np.float32))
+    assert (fast.ok == ref["ok"]).mean() > 0.99 and (fast.z == ref["z"]).mean() > 0.9995
+    both = (fast.ok == 1) & (ref["ok"] == 1)
+    assert (fast.conv_it[both] == ref["conv_it"][both]).mean() > 0.98
+
+
 def test_packed_bits_output():
     code = load_code("wimax_576_0.5")
     llr = awgn_llr(np.random.default_rng(3), 100, code.n, 2.0).astype(np.float32)
