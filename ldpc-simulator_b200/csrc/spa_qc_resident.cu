@@ -330,7 +330,7 @@ bool build_params(const ldpc_graph* g, QcParams<MB, DC>* p)
 
 struct Shape { int mb, dc; };
 // instantiated (MB, DC) shapes, smallest first
-constexpr Shape kShapes[] = { {12, 7}, {6, 15} };
+constexpr Shape kShapes[] = { {12, 7}, {6, 15}, {4, 22} };
 
 int pick_shape(const ldpc_graph* g)
 {
@@ -431,6 +431,7 @@ int qc_resident_decode(const ldpc_graph* g, int64_t frames, int max_iter, unsign
     switch (pick_shape(g)) {
         case 0: return launch_shape<12, 7>(g, frames, max_iter, flags, llr_dev, out, mc, ws, stream);
         case 1: return launch_shape<6, 15>(g, frames, max_iter, flags, llr_dev, out, mc, ws, stream);
+        case 2: return launch_shape<4, 22>(g, frames, max_iter, flags, llr_dev, out, mc, ws, stream);
         default: break;
     }
     set_error("no resident kernel shape for this graph");

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 sys.path.insert(0, HERE)
 
-CODES = ["wimax_2304_0.5", "wimax_576_0.5", "wimax_2304_0.75B"]
+CODES = ["wimax_2304_0.5", "wimax_576_0.5", "wimax_2304_0.75B", "wimax_2304_0.83"]
 
 
 def main():
@@ -32,7 +32,9 @@ def main():
         out.append(dict(name=name, z=int(z), mb=int(sh.shape[0]), nb=int(sh.shape[1]),
                         shift=[[int(v) for v in row] for row in sh]))
     with open(os.path.join(HERE, "csrc", "qc_registry.json"), "w") as f:
-        json.dump(out, f, indent=1)
+        f.write("[\n" + ",\n".join(
+            " {" + f'"name": "{c["name"]}", "z": {c["z"]}, "mb": {c["mb"]}, "nb": {c["nb"]}, "shift": [\n  '
+            + ",\n  ".join(json.dumps(row) for row in c["shift"]) + "]}" for c in out) + "\n]\n")
     print("wrote", len(out), "codes")
 
 

@@ -82,7 +82,7 @@ def load_golden(name):
 
 GOLDEN_DECODE_SETS = ["bch74_std_random", "ccsds128_alist", "ccsds128_std", "tanner155_std", "wifi648_alist",
                       "wimax576_alist", "wimax576_alist_cw", "wimax576_std", "wimax2304_alist",
-                      "wimax2304_075B_alist", "wimax2304_std"]
+                      "wimax2304_075B_alist", "wimax2304_083_alist", "wimax2304_std"]
 
 
 def posterior_violations(got, ref, rel=1e-4, abs_tol=1e-5):

@@ -56,6 +56,7 @@ CODE_FILES = {
     "wimax_576_0.5": "Wimax LDPC Codes/wimax_576_0.5.alist.txt",
     "wimax_2304_0.5": "Wimax LDPC Codes/wimax_2304_0.5.alist.txt",
     "wimax_2304_0.75B": "Wimax LDPC Codes/wimax_2304_0.75B.alist.txt",
+    "wimax_2304_0.83": "Wimax LDPC Codes/wimax_2304_0.83.alist.txt",
 }
 
 
@@ -437,6 +438,9 @@ def main():
                                                 0.5, False, 20, 230401, J),
         "w2304_075B": lambda: build_decode_set("wimax2304_075B_alist", "wimax_2304_0.75B", 16, [2, 3, 4],
                                                0.75, False, 20, 230402, J),
+        # all check degrees even (20): converges under the reference's sign convention -> early termination
+        "w2304_083": lambda: build_decode_set("wimax2304_083_alist", "wimax_2304_0.83", 48, [3.5, 4.0, 4.5, 5.0],
+                                              0.83, False, 20, 230404, J),
         "w2304_std": lambda: build_decode_set("wimax2304_std", "wimax_2304_0.5.std", 8, [5, 6],
                                               0.5, True, 2, 230403, J),
         "bch_mc": lambda: build_bch_mc_anchor(J),

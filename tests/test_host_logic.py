@@ -21,7 +21,7 @@ from results import SimulationConfig, SimulationResult, SNRPointResult
 from settings import Settings
 
 CODES = ["bch_7_4", "ccsds_128_64", "tanner_155_64", "wifi_648_r083", "wimax_576_0.5", "wimax_2304_0.5",
-         "wimax_2304_0.75B"]
+         "wimax_2304_0.75B", "wimax_2304_0.83"]
 
 
 # ---- ALIST ------------------------------------------------------------------------------
@@ -90,7 +90,7 @@ def test_edge_index_is_csr_and_csc_permutation(name):
 
 
 @pytest.mark.parametrize("name,expect", [("wimax_576_0.5", (24, 12, 24, 76)), ("wimax_2304_0.5", (96, 12, 24, 76)),
-                                         ("wimax_2304_0.75B", (96, 6, 24, 88)), ("wifi_648_r083", (27, 4, 24, 88)),
+                                         ("wimax_2304_0.75B", (96, 6, 24, 88)), ("wimax_2304_0.83", (96, 4, 24, 80)), ("wifi_648_r083", (27, 4, 24, 88)),
                                          ("tanner_155_64", (31, 3, 5, 15)), ("bch_7_4", None), ("ccsds_128_64", None)])
 def test_qc_detection(name, expect):
     code = load_code(name)
