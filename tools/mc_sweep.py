@@ -1,0 +1,102 @@
+#!/usr/bin/env python3
+"""Monte-Carlo BER/FER waterfall sweep on 1..8 GPUs (BASELINE.json configs[4]).
+
+    python tools/mc_sweep.py --code wimax_2304_0.5 --snr 1.0 2.0 0.25 --max-frames 2000000 --min-frame-errors 200
+    torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/mc_sweep.py ...
+
+Each rank generates its own frames on its GPU (Philox, stream_id = rank), decodes them with the resident
+kernel and folds the error counters in-kernel; per reporting interval the 5 integer counters are combined
+with ONE NCCL all-reduce and the stopping rule is evaluated on the reduced values.  Rank 0 writes a
+results.json in the reference's schema (results.py) plus the raw counters with Wilson intervals.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "ldpc-simulator_b200"))
+
+import numpy as np  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--code", default="wimax_2304_0.5")
+    ap.add_argument("--alist", default=None, help="ALIST file (overrides --code)")
+    ap.add_argument("--graph", default="alist", choices=["alist", "std"])
+    ap.add_argument("--precision", default="f32_fast", choices=["f64", "f32", "f32_fast"])
+    ap.add_argument("--snr", nargs=3, type=float, default=[1.0, 2.0, 0.5], metavar=("START", "END", "STEP"))
+    ap.add_argument("--speed", type=float, default=0.5)
+    ap.add_argument("--iterations", type=int, default=20)
+    ap.add_argument("--max-frames", type=int, default=1 << 20)
+    ap.add_argument("--min-frame-errors", type=int, default=200)
+    ap.add_argument("--interval-frames", type=int, default=1 << 18)
+    ap.add_argument("--fix-odd-check-sign", action="store_true")
+    ap.add_argument("--no-sigma-sq-quirk", action="store_true")
+    ap.add_argument("--seed", type=int, default=0x5EED)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from encoder_decoder_data import EncoderDecoderData
+    from main import snr_grid
+    from matrix_sparse import SparseMatrix
+    from mc_driver import MonteCarloEngine, wilson_interval
+    from results import SimulationConfig, SimulationResult, SNRPointResult
+    from scipy import sparse
+
+    if a.alist:
+        edd = EncoderDecoderData(a.alist)
+        label = a.alist
+    else:
+        d = np.load(os.path.join(REPO, "tests", "golden", "codes", a.code + ".npz"))
+        h = sparse.csr_matrix((np.ones(d["col_idx"].size, dtype=np.int32), d["col_idx"], d["row_ptr"]),
+                              shape=(int(d["m"]), int(d["n"])))
+        edd = EncoderDecoderData(h=SparseMatrix(sparse_matrix=h))
+        label = a.code
+    eng = MonteCarloEngine(edd, graph=a.graph, precision=a.precision, max_iterations=a.iterations,
+                           fix_odd_check_sign=a.fix_odd_check_sign, sigma_sq_quirk=not a.no_sigma_sq_quirk, seed=a.seed)
+    t0 = time.time()
+    points, raw = [], []
+    for snr in snr_grid(*a.snr):
+        t1 = time.time()
+        c = eng.run_point(snr, a.speed, max_frames=a.max_frames, min_frame_errors=a.min_frame_errors,
+                          interval_frames=a.interval_frames)
+        dt = time.time() - t1
+        if rank == 0:
+            flo, fhi = wilson_interval(c.frame_errors, c.frames)
+            blo, bhi = wilson_interval(c.bit_errors, c.frames * edd._k)
+            raw.append(dict(snr_db=snr, frames=c.frames, frame_errors=c.frame_errors, bit_errors=c.bit_errors,
+                            fer=c.fer(), fer_ci=[flo, fhi], ber=c.ber(edd._k), ber_ci=[blo, bhi],
+                            avg_conv=c.avg_conv(), seconds=dt, info_gbit_per_s=c.frames * edd._k / dt / 1e9))
+            print(json.dumps(raw[-1]), flush=True)
+            points.append(SNRPointResult(snr_db=snr, ber=c.ber(edd._k), fer=c.fer(), avg_normalized_llr=0.0,
+                                         total_blocks=c.frames, successful_blocks=c.frames - c.frame_errors,
+                                         failed_blocks=c.frame_errors, avg_convergence_iterations=c.avg_conv(),
+                                         matrix_path=label, modulation=1, max_iterations=a.iterations,
+                                         interleaver="none", encoding_method="standard"))
+    if rank == 0 and a.out:
+        cfg = SimulationConfig(matrix_path=label, n=edd._n, m=edd._m, k=edd._k, rate=edd._rate, blocks=a.max_frames,
+                               max_iterations=a.iterations, encoding_method="standard", interleaver_type="none",
+                               decoder_type="sumproduct", channel_mode=1, modulation=1, speed=a.speed,
+                               snr_range=tuple(a.snr), threads=world, timestamp=time.strftime("%Y-%m-%dT%H:%M:%S"))
+        SimulationResult(config=cfg, snr_points=points, wall_clock_seconds=time.time() - t0).to_json(a.out)
+        with open(a.out + ".counters.json", "w") as f:
+            json.dump(dict(world=world, points=raw), f, indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
