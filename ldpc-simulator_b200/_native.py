@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libldpc_b200.so")
+LIB_PATH = os.path.join(_HERE, "lib", os.environ.get("LDPC_LIB_NAME", "libldpc_b200.so"))
 
 LDPC_F64, LDPC_F32, LDPC_F32_FAST = 0, 1, 2
 FLAG_EARLY_TERM, FLAG_COMPACT, FLAG_FIX_ODD_SIGN, FLAG_FORCE_GENERIC, FLAG_TABLE_KERNEL = 0x1, 0x2, 0x4, 0x8, 0x10

@@ -11,14 +11,18 @@ namespace ldpc {
 
 namespace {
 
-template <class C, bool EARLY, int THREADS, int MINB, bool SPLIT = false>
+template <class C, bool EARLY, int THREADS, int MINB, bool SPLIT = false, int REGS = 0>
 int launch_spec(C code, const ldpc_graph* g, int64_t frames, int max_iter, unsigned flags, const float* llr,
                 const qc::Outputs& out, const McParams& mc, void* ws, cudaStream_t stream)
 {
     DeviceInfo di;
     int rc = get_device_info(&di);
     if (rc) return rc;
+#ifdef LDPC_QC_TUNING
+    auto kp = [] { if constexpr (REGS > 0) return qc::k_qc_spec_regs<THREADS, REGS, EARLY, C>; else return qc::k_qc_spec<THREADS, MINB, EARLY, SPLIT, C>; }();
+#else
     auto kp = qc::k_qc_spec<THREADS, MINB, EARLY, SPLIT, C>;
+#endif
     const size_t smem = sizeof(float) * 3 * (size_t)C::N;
     static thread_local bool configured = false;
     static thread_local int per_sm = 0;
@@ -29,7 +33,11 @@ int launch_spec(C code, const ldpc_graph* g, int64_t frames, int max_iter, unsig
         configured = true;
     }
     if (per_sm < 1) { set_error("specialised resident kernel does not fit on an SM"); return LDPC_ERR_UNSUPPORTED; }
-    const int grid = (int)std::min<int64_t>(frames, (int64_t)per_sm * di.sm_count);
+    int ctas_per_sm = per_sm;
+#ifdef LDPC_QC_TUNING
+    if (const char* e = getenv("LDPC_QC_MAX_CTAS")) ctas_per_sm = std::max(1, std::min(per_sm, atoi(e)));
+#endif
+    const int grid = (int)std::min<int64_t>(frames, (int64_t)ctas_per_sm * di.sm_count);
     unsigned long long* counter = nullptr;
     if (EARLY) {
         if (!ws) { set_error("early termination needs a workspace (work counter)"); return LDPC_ERR_WORKSPACE; }
@@ -69,6 +77,9 @@ int launch_code(C code, const Args& a)
     if (T == 192) {
         const char* e = getenv("LDPC_QC_MINB");
         const int want = e ? atoi(e) : B;
+        const int regs = getenv("LDPC_QC_REGS") ? atoi(getenv("LDPC_QC_REGS")) : 0;
+#define LDPC_GO3(RR) do { if (regs == RR) { return early ? launch_spec<C, true, T, 1, false, RR>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream) : launch_spec<C, false, T, 1, false, RR>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream); } } while (0)
+        LDPC_GO3(80); LDPC_GO3(96); LDPC_GO3(104); LDPC_GO3(112); LDPC_GO3(128);
         const bool split = getenv("LDPC_QC_SPLIT") && atoi(getenv("LDPC_QC_SPLIT"));
 #define LDPC_GO2(BB) do { if (split) { return early ? launch_spec<C, true, T, BB, true>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream) : launch_spec<C, false, T, BB, true>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream); } } while (0)
         if (want == 2) { LDPC_GO2(2); LDPC_GO(2); }
