@@ -107,6 +107,30 @@ def test_f64_kernel_matches_oracle(name, frames, max_iter, snrs):
     assert (ref["conv_it"] > 0).any() or name.startswith("wimax")      # the batch exercises late convergence
 
 
+def test_config1_full_batch_64k_frames_against_oracle():
+    """BASELINE.json configs[1]: WiMAX-576 r1/2, 20 passes, 65 536 frames in one call, mix of Eb/N0
+    (1, 2, 3, 4, 6 dB) so that non-converged and saturated regimes are hit; identical LLRs go to the fp64
+    CUDA kernels and to the pinned oracle.  Bar: decisions / iteration / syndrome identical on >= 99.99 %
+    of the frames, posterior within 1e-4 relative or 1e-5 absolute."""
+    code = load_code("wimax_576_0.5")
+    rng = np.random.default_rng(20261018)
+    frames = 65536
+    llr = awgn_llr(rng, frames, code.n, np.resize(np.array([1.0, 2.0, 3.0, 4.0, 6.0]), frames))
+    ref = oracle(code, llr, 20)
+    res = make_decoder(code, 20).decode_batch(llr, want_posterior=True)
+    bad = frame_mismatch(res, ref)
+    assert bad.mean() <= 1e-4, f"{bad.sum()} of {frames} frames differ"
+    viol = posterior_violations(res.post, ref["post"]).any(axis=1)
+    assert viol.mean() <= 1e-4, f"{viol.sum()} frames outside the posterior tolerance"
+    # the graph main.py really decodes on (H_std, 41 278 edges): 4 096 of those frames' worth of LLRs
+    std = load_code("wimax_576_0.5.std")
+    sub = llr[:4096]
+    ref_s = oracle(std, sub, 20)
+    res_s = make_decoder(std, 20).decode_batch(sub, want_posterior=True)
+    assert frame_mismatch(res_s, ref_s).mean() <= 1e-4
+    assert posterior_violations(res_s.post, ref_s["post"]).any(axis=1).mean() <= 1e-3
+
+
 def test_compaction_and_chunking_do_not_change_results():
     code = load_code("ccsds_128_64")
     rng = np.random.default_rng(5)
