@@ -5,24 +5,19 @@
 #include "qc_codes_gen.cuh"
 
 #include <algorithm>
-#include <cstdlib>
 
 namespace ldpc {
 
 namespace {
 
-template <class C, bool EARLY, int THREADS, int MINB, bool SPLIT = false, int REGS = 0>
+template <class C, bool EARLY, int THREADS, int MINB>
 int launch_spec(C code, const ldpc_graph* g, int64_t frames, int max_iter, unsigned flags, const float* llr,
                 const qc::Outputs& out, const McParams& mc, void* ws, cudaStream_t stream)
 {
     DeviceInfo di;
     int rc = get_device_info(&di);
     if (rc) return rc;
-#ifdef LDPC_QC_TUNING
-    auto kp = [] { if constexpr (REGS > 0) return qc::k_qc_spec_regs<THREADS, REGS, EARLY, C>; else return qc::k_qc_spec<THREADS, MINB, EARLY, SPLIT, C>; }();
-#else
-    auto kp = qc::k_qc_spec<THREADS, MINB, EARLY, SPLIT, C>;
-#endif
+    auto kp = qc::k_qc_spec<THREADS, MINB, EARLY, C>;
     const size_t smem = sizeof(float) * 3 * (size_t)C::N;
     static thread_local bool configured = false;
     static thread_local int per_sm = 0;
@@ -33,11 +28,7 @@ int launch_spec(C code, const ldpc_graph* g, int64_t frames, int max_iter, unsig
         configured = true;
     }
     if (per_sm < 1) { set_error("specialised resident kernel does not fit on an SM"); return LDPC_ERR_UNSUPPORTED; }
-    int ctas_per_sm = per_sm;
-#ifdef LDPC_QC_TUNING
-    if (const char* e = getenv("LDPC_QC_MAX_CTAS")) ctas_per_sm = std::max(1, std::min(per_sm, atoi(e)));
-#endif
-    const int grid = (int)std::min<int64_t>(frames, (int64_t)ctas_per_sm * di.sm_count);
+    const int grid = (int)std::min<int64_t>(frames, (int64_t)per_sm * di.sm_count);
     unsigned long long* counter = nullptr;
     if (EARLY) {
         if (!ws) { set_error("early termination needs a workspace (work counter)"); return LDPC_ERR_WORKSPACE; }
@@ -69,26 +60,8 @@ int launch_code(C code, const Args& a)
     constexpr int NEED = 2 * C::MAXSLOT + 60;
     constexpr int B0 = 65536 / (T * (NEED > 168 ? 255 : 168));
     constexpr int B = B0 < 1 ? 1 : (B0 > 32 ? 32 : B0);
-#define LDPC_GO(BB)                                                                                                  \
-    return early ? launch_spec<C, true, T, BB>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream) \
-                 : launch_spec<C, false, T, BB>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream)
-#ifdef LDPC_QC_TUNING
-    // tuning builds only: LDPC_QC_MINB selects the occupancy target of the 96-thread kernels
-    if (T == 192) {
-        const char* e = getenv("LDPC_QC_MINB");
-        const int want = e ? atoi(e) : B;
-        const int regs = getenv("LDPC_QC_REGS") ? atoi(getenv("LDPC_QC_REGS")) : 0;
-#define LDPC_GO3(RR) do { if (regs == RR) { return early ? launch_spec<C, true, T, 1, false, RR>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream) : launch_spec<C, false, T, 1, false, RR>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream); } } while (0)
-        LDPC_GO3(80); LDPC_GO3(96); LDPC_GO3(104); LDPC_GO3(112); LDPC_GO3(128);
-        const bool split = getenv("LDPC_QC_SPLIT") && atoi(getenv("LDPC_QC_SPLIT"));
-#define LDPC_GO2(BB) do { if (split) { return early ? launch_spec<C, true, T, BB, true>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream) : launch_spec<C, false, T, BB, true>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream); } } while (0)
-        if (want == 2) { LDPC_GO2(2); LDPC_GO(2); }
-        if (want == 3) { LDPC_GO2(3); LDPC_GO(3); }
-        if (want == 4) { LDPC_GO2(4); LDPC_GO(4); }
-    }
-#endif
-    LDPC_GO(B);
-#undef LDPC_GO
+    return early ? launch_spec<C, true, T, B>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream)
+                 : launch_spec<C, false, T, B>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream);
 }
 
 }  // namespace

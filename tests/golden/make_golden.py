@@ -365,6 +365,27 @@ def build_bch_mc_anchor(jobs, blocks_per_point=40000):
         json.dump(out, f, indent=1, sort_keys=True)
 
 
+def build_w576_mc_anchor(jobs):
+    """Reference Monte-Carlo anchors for the graph main.py really decodes on (H_std of WiMAX-576 r1/2),
+    its own conventions (sigma^2 quirk, speed 0.5, 20 passes).  Slow: ~17 s per frame at 0 dB."""
+    path = os.path.join(DB, CODE_FILES["wimax_576_0.5"])
+    plan = {0.0: 40, 3.0: 40, 4.0: 60, 5.0: 120}          # frames per worker
+    pts = {}
+    for snr, per in plan.items():
+        tasks = [(path, 0.5, snr, per, 20, 57600 + int(snr) * 100 + w) for w in range(jobs)]
+        with ProcessPoolExecutor(max_workers=jobs) as ex:
+            res = list(ex.map(_mc_worker, tasks))
+        p = dict(frames=0, frame_err=0, bit_err=0, conv_sum=0, conv_cnt=0, per_worker_bit_err=[], per_worker_frames=per)
+        for _snr, blocks, fail, biterr, convsum, convcnt in res:
+            p["frames"] += blocks; p["frame_err"] += fail; p["bit_err"] += biterr
+            p["conv_sum"] += convsum; p["conv_cnt"] += convcnt; p["per_worker_bit_err"].append(biterr)
+        pts[str(snr)] = p
+        log(f"w576 std mc {snr} dB: frames {p['frames']} FER {p['frame_err']/p['frames']:.4f} "
+            f"BER {p['bit_err']/(288*p['frames']):.5f}")
+        with open(os.path.join(HERE, "wimax576_std_mc_anchor.json"), "w") as f:
+            json.dump(dict(speed=0.5, max_iter=20, k=288, n=576, points=pts), f, indent=1, sort_keys=True)
+
+
 def build_results_sample():
     """results.py writers on fixed inputs -> byte-exact expected JSON / CSV text."""
     from results import SimulationResult, SimulationConfig, SNRPointResult
@@ -444,6 +465,7 @@ def main():
         "w2304_std": lambda: build_decode_set("wimax2304_std", "wimax_2304_0.5.std", 8, [5, 6],
                                               0.5, True, 2, 230403, J),
         "bch_mc": lambda: build_bch_mc_anchor(J),
+        "w576_mc": lambda: build_w576_mc_anchor(J),
     }
     for name, fn in steps.items():
         if a.only and name not in a.only:
