@@ -18,7 +18,7 @@ int launch_spec(C code, const ldpc_graph* g, int64_t frames, int max_iter, unsig
     int rc = get_device_info(&di);
     if (rc) return rc;
     auto kp = qc::k_qc_spec<THREADS, MINB, EARLY, C>;
-    const size_t smem = sizeof(float) * 3 * (size_t)C::N;
+    const size_t smem = sizeof(float) * 4 * (size_t)C::N;      // channel + 2 posteriors + TMA stage
     static thread_local bool configured = false;
     static thread_local int per_sm = 0;
     if (!configured) {
