@@ -156,6 +156,43 @@ def test_compaction_and_chunking_do_not_change_results():
     assert (d.ok == (d.conv_it == 19)).all()
 
 
+@pytest.mark.parametrize("maxdeg", [6, 20, 40])
+def test_irregular_graphs_with_degenerate_nodes(maxdeg):
+    """Degree-1 checks (leave-one-out of nothing: the clipped atanh of 1), an empty check row, a variable
+    without any check, rows up to degree 40 (register and two-sweep check-node variants), LLRs that are
+    exactly zero, huge, and negative zero -- all must follow the reference's arithmetic (oracle)."""
+    from scipy import sparse
+
+    class Code:
+        pass
+
+    rng = np.random.default_rng(1000 + maxdeg)
+    n, m = 96, 48
+    dense = np.zeros((m, n), dtype=np.int32)
+    for i in range(m):
+        d = int(rng.integers(2, maxdeg + 1))
+        dense[i, rng.choice(n - 1, size=d, replace=False)] = 1          # column n-1 stays unconnected
+    dense[0] = 0; dense[0, 5] = 1                                        # degree-1 check
+    dense[1] = 0                                                         # empty check
+    dense[2] = 0; dense[2, :maxdeg] = 1                                  # the widest row
+    h = sparse.csr_matrix(dense); h.sort_indices()
+    code = Code()
+    code.n, code.m = n, m
+    code.row_ptr, code.col_idx = h.indptr.astype(np.int32), h.indices.astype(np.int32)
+    code.csr = lambda: h
+    frames = 512
+    llr = awgn_llr(rng, frames, n, np.resize(np.array([0.0, 3.0, 8.0]), frames))
+    llr[::7, ::5] = 0.0
+    llr[::11, 3] = -0.0
+    llr[::13, ::9] = 80.0
+    llr[::17, 1::9] = -1e-12
+    ref = oracle(code, llr, 12)
+    for compact in (False, True):
+        res = make_decoder(code, 12).decode_batch(llr, want_posterior=True, compact=compact)
+        assert not frame_mismatch(res, ref).any()
+        assert not posterior_violations(res.post, ref["post"]).any()
+
+
 def test_ragged_and_edge_inputs():
     import _native
     code = load_code("bch_7_4.std")
