@@ -182,7 +182,9 @@ int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t frames, int m
  *   seed, stream_id, frame_offset
  *                      Philox key = seed; counter = (stream_id, frame_offset + frame, word) so that
  *                      ranks / launches draw disjoint streams
- *   codeword_dev       [n] uint8 transmitted codeword in graph-column order, NULL = all-zero
+ *   codeword_dev       uint8 transmitted codeword(s) in graph-column order, NULL = all-zero
+ *   codeword_stride    0: one codeword [n] for every frame; >= n: frame f sends codeword_dev + f*stride
+ *                      (e.g. the output of ldpc_encode_batch)
  *   info_mask_dev      [n] uint8, 1 = information position; NULL = the first k_info positions
  *   k_info             number of information bits; BER is taken over them (main.py:323-330)
  *   counters_dev       uint64[5], ACCUMULATED: frames, failed frames, info-bit errors counted in
@@ -192,7 +194,7 @@ int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t frames, int m
 int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
                 double speed, double snr_db, int sigma_sq_quirk,
                 uint64_t seed, uint32_t stream_id, uint64_t frame_offset,
-                const uint8_t* codeword_dev, const uint8_t* info_mask_dev, int k_info,
+                const uint8_t* codeword_dev, int64_t codeword_stride, const uint8_t* info_mask_dev, int k_info,
                 uint64_t* counters_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* Workspace for ldpc_mc_run (it also holds the generated LLRs and decoder outputs). */
@@ -202,7 +204,32 @@ size_t ldpc_mc_workspace_bytes(const ldpc_graph* g, int64_t frames, int dtype);
  * output ldpc_mc_run would decode -- used by the tests to feed identical frames to the oracle. */
 int ldpc_channel_llr(int n, int dtype, int64_t frames, double speed, double snr_db, int sigma_sq_quirk,
                      uint64_t seed, uint32_t stream_id, uint64_t frame_offset,
-                     const uint8_t* codeword_dev, void* llr_dev, void* stream);
+                     const uint8_t* codeword_dev, int64_t codeword_stride, void* llr_dev, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Systematic encoder on the device (random-codeword Monte-Carlo).
+ * ------------------------------------------------------------------------- */
+typedef struct ldpc_encoder ldpc_encoder;
+
+/*
+ * Encoder for H_std = [A | I_m] as produced by ldpc_host_standard_form (h_std_bits [m][(n+63)/64]).
+ * Replaces create_generator_matrix + DataBuffer.encode (encoder_decoder_data.py:319-344,
+ * data_buffer.py:47-82): codeword in H_std column order = [u | A u mod 2].  out_pos (may be NULL)
+ * gives, for every H_std column j, the position it is written to -- pass the column permutation of
+ * the standard form to obtain codewords in raw ALIST order.
+ */
+int ldpc_encoder_create(int m, int n, const uint64_t* h_std_bits, const int32_t* out_pos, ldpc_encoder** out);
+void ldpc_encoder_destroy(ldpc_encoder* e);
+
+/*
+ * Encode `frames` frames.  data_dev [frames][k] uint8 info bits, or NULL to draw them on the device
+ * (Philox, replaces Generator.generate_bit_sequence, generator.py:7-9; key = seed, counters disjoint
+ * from the noise of the same stream_id / frame).  data_out_dev [frames][k] (may be NULL) receives the
+ * info bits; codeword_dev [frames][n] the codewords.  Asynchronous on `stream`.
+ */
+int ldpc_encode_batch(const ldpc_encoder* e, int64_t frames, const uint8_t* data_dev, uint64_t seed,
+                      uint32_t stream_id, uint64_t frame_offset, uint8_t* data_out_dev,
+                      uint8_t* codeword_dev, void* stream);
 
 /* Number of kernels this library launched since it was loaded (bench.py's gpu_launches). */
 uint64_t ldpc_kernel_launch_count(void);

@@ -21,7 +21,8 @@ EXPORTS = [
     "ldpc_host_edge_index", "ldpc_host_detect_qc", "ldpc_host_standard_form",
     "ldpc_graph_create_csr", "ldpc_graph_create_qc", "ldpc_graph_info", "ldpc_graph_qc_shifts",
     "ldpc_graph_destroy", "ldpc_workspace_bytes", "ldpc_decode_batch", "ldpc_decode_batch_host",
-    "ldpc_mc_run", "ldpc_mc_workspace_bytes", "ldpc_channel_llr", "ldpc_kernel_launch_count",
+    "ldpc_mc_run", "ldpc_mc_workspace_bytes", "ldpc_channel_llr", "ldpc_encoder_create", "ldpc_encoder_destroy",
+    "ldpc_encode_batch", "ldpc_kernel_launch_count",
     "ldpc_measure_mufu_peak", "ldpc_last_error", "ldpc_abi_version",
 ]
 
@@ -70,10 +71,13 @@ def lib():
                                         vp, C.c_size_t, vp]),
         "ldpc_decode_batch_host": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_uint, vp, vp, vp, vp, vp, vp, vp, C.c_int]),
         "ldpc_mc_run": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_uint, C.c_double, C.c_double, C.c_int,
-                                  C.c_uint64, C.c_uint32, C.c_uint64, vp, vp, C.c_int, vp, vp, C.c_size_t, vp]),
+                                  C.c_uint64, C.c_uint32, C.c_uint64, vp, i64, vp, C.c_int, vp, vp, C.c_size_t, vp]),
         "ldpc_mc_workspace_bytes": (C.c_size_t, [vp, i64, C.c_int]),
         "ldpc_channel_llr": (C.c_int, [C.c_int, C.c_int, i64, C.c_double, C.c_double, C.c_int, C.c_uint64,
-                                       C.c_uint32, C.c_uint64, vp, vp, vp]),
+                                       C.c_uint32, C.c_uint64, vp, i64, vp, vp]),
+        "ldpc_encoder_create": (C.c_int, [C.c_int, C.c_int, u64p, i32p, C.POINTER(vp)]),
+        "ldpc_encoder_destroy": (None, [vp]),
+        "ldpc_encode_batch": (C.c_int, [vp, i64, vp, C.c_uint64, C.c_uint32, C.c_uint64, vp, vp, vp]),
         "ldpc_kernel_launch_count": (C.c_uint64, []),
         "ldpc_measure_mufu_peak": (C.c_int, [C.POINTER(C.c_double), vp]),
         "ldpc_last_error": (C.c_char_p, []),

@@ -73,13 +73,18 @@ class Channel:
             speed, snr_db = self._speed, self._snr_db
         tdt = torch.float64 if dtype == "f64" else torch.float32
         out = torch.empty((frames, n), dtype=tdt, device="cuda")
-        cw = None
-        if codeword is not None:
-            cw = torch.as_tensor(np.asarray(codeword, dtype=np.uint8)).cuda()
+        cw, stride = None, 0
+        if codeword is not None:          # [n]: one codeword for every frame; [frames, n]: one per frame
+            cw = (codeword if hasattr(codeword, "data_ptr") else torch.as_tensor(np.asarray(codeword, dtype=np.uint8)))
+            cw = cw.to(device="cuda", dtype=torch.uint8).contiguous()
+            if cw.dim() == 2:
+                if tuple(cw.shape) != (frames, n):
+                    raise ValueError(f"per-frame codewords must be [{frames}, {n}]")
+                stride = n
         _native.check(_native.lib().ldpc_channel_llr(
             n, _native.LDPC_F64 if dtype == "f64" else _native.LDPC_F32, frames, float(speed), float(snr_db),
             int(self.sigma_sq_quirk), int(seed), int(stream_id), int(frame_offset),
-            cw.data_ptr() if cw is not None else None, out.data_ptr(),
+            cw.data_ptr() if cw is not None else None, stride, out.data_ptr(),
             torch.cuda.current_stream().cuda_stream))
         return out
 

@@ -73,10 +73,6 @@ bool is_pinned(const void* p)
     return a.type == cudaMemoryTypeHost;
 }
 
-int decode_device(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
-                  const void* llr, uint8_t* z, uint32_t* zbits, int32_t* conv, uint8_t* ok, void* post,
-                  float* norm, int k_info, void* ws, size_t ws_bytes, cudaStream_t stream);
-
 __global__ void k_pack_bits(const uint8_t* __restrict__ z, int n, int64_t frames, uint32_t* __restrict__ zbits)
 {
     const int words = (n + 31) / 32;
@@ -91,11 +87,6 @@ __global__ void k_pack_bits(const uint8_t* __restrict__ z, int n, int64_t frames
         }
         zbits[id] = v;
     }
-}
-
-__global__ void k_norm_zero(float* norm, int64_t frames)
-{
-    for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < frames; f += (int64_t)gridDim.x * blockDim.x) norm[f] = 0.f;
 }
 
 int decode_device(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
@@ -302,14 +293,16 @@ extern "C" size_t ldpc_mc_workspace_bytes(const ldpc_graph* g, int64_t frames, i
 extern "C" int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
                            double speed, double snr_db, int sigma_sq_quirk,
                            uint64_t seed, uint32_t stream_id, uint64_t frame_offset,
-                           const uint8_t* codeword_dev, const uint8_t* info_mask_dev, int k_info,
-                           uint64_t* counters_dev, void* workspace_dev, size_t workspace_bytes, void* stream_v)
+                           const uint8_t* codeword_dev, int64_t codeword_stride, const uint8_t* info_mask_dev,
+                           int k_info, uint64_t* counters_dev, void* workspace_dev, size_t workspace_bytes,
+                           void* stream_v)
 {
     int rc = check_common(g, dtype, frames, max_iter);
     if (rc) return rc;
     if (!counters_dev) { set_error("null counters"); return LDPC_ERR_INVALID; }
     if (!(speed > 0.0)) { set_error("speed must be positive"); return LDPC_ERR_INVALID; }
     if (k_info < 0 || k_info > g->n) { set_error("k_info out of range"); return LDPC_ERR_INVALID; }
+    if (codeword_stride != 0 && codeword_stride < g->n) { set_error("codeword_stride must be 0 or >= n"); return LDPC_ERR_INVALID; }
     if (frames == 0) return LDPC_OK;
     cudaStream_t stream = (cudaStream_t)stream_v;
     if (use_resident(g, dtype, flags)) {
@@ -318,6 +311,7 @@ extern "C" int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int m
         channel_params(speed, snr_db, sigma_sq_quirk, seed, stream_id, &mc);
         mc.frame_offset = frame_offset;
         mc.codeword = codeword_dev;
+        mc.codeword_stride = codeword_stride;
         mc.info_mask = info_mask_dev;
         mc.k_info = k_info;
         mc.counters = (unsigned long long*)counters_dev;
@@ -351,11 +345,12 @@ extern "C" int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int m
     for (int64_t f0 = 0; f0 < frames; f0 += chunk) {
         const int64_t c = std::min<int64_t>(chunk, frames - f0);
         rc = channel_fill(n, gd, c, speed, snr_db, sigma_sq_quirk, seed, stream_id, frame_offset + (uint64_t)f0,
-                          codeword_dev, llr, stream);
+                          codeword_dev ? codeword_dev + f0 * codeword_stride : nullptr, codeword_stride, llr, stream);
         if (rc) return rc;
         rc = generic_decode(g, gd, c, max_iter, flags, llr, z, conv, ok, nullptr, nullptr, 0, p, ws_bytes, stream);
         if (rc) return rc;
-        rc = count_errors(n, k_info, c, z, ok, conv, codeword_dev, info_mask_dev, (unsigned long long*)counters_dev, stream);
+        rc = count_errors(n, k_info, c, z, ok, conv, codeword_dev ? codeword_dev + f0 * codeword_stride : nullptr, codeword_stride,
+                          info_mask_dev, (unsigned long long*)counters_dev, stream);
         if (rc) return rc;
     }
     return LDPC_OK;
@@ -363,10 +358,10 @@ extern "C" int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int m
 
 extern "C" int ldpc_channel_llr(int n, int dtype, int64_t frames, double speed, double snr_db, int sigma_sq_quirk,
                                 uint64_t seed, uint32_t stream_id, uint64_t frame_offset,
-                                const uint8_t* codeword_dev, void* llr_dev, void* stream)
+                                const uint8_t* codeword_dev, int64_t codeword_stride, void* llr_dev, void* stream)
 {
     return channel_fill(n, dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32, frames, speed, snr_db, sigma_sq_quirk, seed,
-                        stream_id, frame_offset, codeword_dev, llr_dev, (cudaStream_t)stream);
+                        stream_id, frame_offset, codeword_dev, codeword_stride, llr_dev, (cudaStream_t)stream);
 }
 
 extern "C" int ldpc_measure_mufu_peak(double* ops_per_s, void* stream_v)

@@ -93,7 +93,8 @@ struct McParams {               // in-kernel channel (awgn_philox.cuh); enabled 
     uint64_t seed = 0;
     uint32_t stream_id = 0;
     uint64_t frame_offset = 0;
-    const uint8_t* codeword = nullptr;       // device, [n] or null = all-zero
+    const uint8_t* codeword = nullptr;       // device, [n] (or [frames][n]) or null = all-zero
+    long long codeword_stride = 0;           // bytes between the codewords of consecutive frames, 0 = one for all
     const uint8_t* info_mask = nullptr;      // device, [n] or null = first k_info positions
     int k_info = 0;
     unsigned long long* counters = nullptr;  // device uint64[5]
@@ -112,11 +113,11 @@ int qc_spec_decode(int idx, const ldpc_graph* g, int64_t frames, int max_iter, u
 
 // ---- channel / counters, mc.cu ---------------------------------------------
 int channel_fill(int n, int dtype, int64_t frames, double speed, double snr_db, int quirk, uint64_t seed,
-                 uint32_t stream_id, uint64_t frame_offset, const uint8_t* codeword_dev, void* llr_dev,
-                 cudaStream_t stream);
+                 uint32_t stream_id, uint64_t frame_offset, const uint8_t* codeword_dev, int64_t codeword_stride,
+                 void* llr_dev, cudaStream_t stream);
 void channel_params(double speed, double snr_db, int quirk, uint64_t seed, uint32_t stream_id, McParams* mc);
 int count_errors(int n, int k_info, int64_t frames, const uint8_t* z_dev, const uint8_t* ok_dev,
-                 const int32_t* conv_dev, const uint8_t* codeword_dev, const uint8_t* info_mask_dev,
-                 unsigned long long* counters_dev, cudaStream_t stream);
+                 const int32_t* conv_dev, const uint8_t* codeword_dev, int64_t codeword_stride,
+                 const uint8_t* info_mask_dev, unsigned long long* counters_dev, cudaStream_t stream);
 
 }  // namespace ldpc

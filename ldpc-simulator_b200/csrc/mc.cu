@@ -17,7 +17,7 @@ namespace {
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_channel_fill(int n, int64_t frames, ChannelConst cc, uint64_t frame_offset,
-               const uint8_t* __restrict__ codeword, T* __restrict__ llr)
+               const uint8_t* __restrict__ codeword_base, long long cw_stride, T* __restrict__ llr)
 {
     const int quads = (n + 3) / 4;
     const int64_t items = frames * quads;
@@ -26,7 +26,8 @@ k_channel_fill(int n, int64_t frames, ChannelConst cc, uint64_t frame_offset,
         const int64_t f = id / quads;
         const uint32_t q = (uint32_t)(id - f * quads);
         uint32_t bits = 0;
-        if (codeword) {
+        if (codeword_base) {
+            const uint8_t* codeword = codeword_base + f * cw_stride;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 if ((int)(4 * q + i) < n && codeword[4 * q + i]) bits |= 1u << i;
@@ -43,8 +44,8 @@ k_channel_fill(int n, int64_t frames, ChannelConst cc, uint64_t frame_offset,
 __global__ void __launch_bounds__(256)
 k_count_errors(int n, int k_info, int64_t frames, const uint8_t* __restrict__ z,
                const uint8_t* __restrict__ ok, const int32_t* __restrict__ conv,
-               const uint8_t* __restrict__ codeword, const uint8_t* __restrict__ info_mask,
-               unsigned long long* __restrict__ counters)
+               const uint8_t* __restrict__ codeword_base, long long cw_stride,
+               const uint8_t* __restrict__ info_mask, unsigned long long* __restrict__ counters)
 {
     __shared__ unsigned long long acc[5];
     if (threadIdx.x < 5) acc[threadIdx.x] = 0;
@@ -56,6 +57,7 @@ k_count_errors(int n, int k_info, int64_t frames, const uint8_t* __restrict__ z,
     for (int64_t f = warp0; f < frames; f += nwarps) {
         const bool good = ok[f] != 0;
         if (!good) {                                                     // main.py:326
+            const uint8_t* codeword = codeword_base ? codeword_base + f * cw_stride : nullptr;
             int errs = 0;
             const int span = info_mask ? n : k_info;
             for (int j = lane; j < span; j += 32) {
@@ -97,8 +99,8 @@ static ChannelConst make_channel_const(double speed, double snr_db, int quirk, u
 }
 
 int channel_fill(int n, int dtype, int64_t frames, double speed, double snr_db, int quirk, uint64_t seed,
-                 uint32_t stream_id, uint64_t frame_offset, const uint8_t* codeword_dev, void* llr_dev,
-                 cudaStream_t stream)
+                 uint32_t stream_id, uint64_t frame_offset, const uint8_t* codeword_dev, int64_t codeword_stride,
+                 void* llr_dev, cudaStream_t stream)
 {
     if (n <= 0 || frames < 0 || !llr_dev || !(speed > 0.0)) { set_error("bad channel arguments"); return LDPC_ERR_INVALID; }
     if (frames == 0) return LDPC_OK;
@@ -109,9 +111,9 @@ int channel_fill(int n, int dtype, int64_t frames, double speed, double snr_db, 
     const int64_t items = frames * ((n + 3) / 4);
     const int grid = (int)std::min<int64_t>((items + 255) / 256, (int64_t)di.sm_count * 16);
     if (dtype == LDPC_F64)
-        k_channel_fill<double><<<grid, 256, 0, stream>>>(n, frames, cc, frame_offset, codeword_dev, (double*)llr_dev);
+        k_channel_fill<double><<<grid, 256, 0, stream>>>(n, frames, cc, frame_offset, codeword_dev, codeword_stride, (double*)llr_dev);
     else
-        k_channel_fill<float><<<grid, 256, 0, stream>>>(n, frames, cc, frame_offset, codeword_dev, (float*)llr_dev);
+        k_channel_fill<float><<<grid, 256, 0, stream>>>(n, frames, cc, frame_offset, codeword_dev, codeword_stride, (float*)llr_dev);
     LDPC_LAUNCH_CHECK();
     return LDPC_OK;
 }
@@ -126,15 +128,15 @@ void channel_params(double speed, double snr_db, int quirk, uint64_t seed, uint3
 }
 
 int count_errors(int n, int k_info, int64_t frames, const uint8_t* z_dev, const uint8_t* ok_dev,
-                 const int32_t* conv_dev, const uint8_t* codeword_dev, const uint8_t* info_mask_dev,
-                 unsigned long long* counters_dev, cudaStream_t stream)
+                 const int32_t* conv_dev, const uint8_t* codeword_dev, int64_t codeword_stride,
+                 const uint8_t* info_mask_dev, unsigned long long* counters_dev, cudaStream_t stream)
 {
     if (frames == 0) return LDPC_OK;
     DeviceInfo di;
     int rc = get_device_info(&di);
     if (rc) return rc;
     const int grid = (int)std::min<int64_t>((frames * 32 + 255) / 256, (int64_t)di.sm_count * 8);
-    k_count_errors<<<grid, 256, 0, stream>>>(n, k_info, frames, z_dev, ok_dev, conv_dev, codeword_dev, info_mask_dev, counters_dev);
+    k_count_errors<<<grid, 256, 0, stream>>>(n, k_info, frames, z_dev, ok_dev, conv_dev, codeword_dev, codeword_stride, info_mask_dev, counters_dev);
     LDPC_LAUNCH_CHECK();
     return LDPC_OK;
 }

@@ -116,9 +116,10 @@ k_qc_resident(const __grid_constant__ QcParams<MB, DC> p, const float* __restric
             for (int q = threadIdx.x; q < (n + 3) / 4; q += THREADS) {
                 uint32_t bits = 0;
                 if (mc.codeword) {
+                    const uint8_t* cw = mc.codeword + f * mc.codeword_stride;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        if (4 * q + i < n && mc.codeword[4 * q + i]) bits |= 1u << i;
+                        if (4 * q + i < n && cw[4 * q + i]) bits |= 1u << i;
                 }
                 float v[4];
                 channel_llr4(cc, mc.frame_offset + (uint64_t)f, (uint32_t)q, bits, v);
@@ -278,7 +279,7 @@ k_qc_resident(const __grid_constant__ QcParams<MB, DC> p, const float* __restric
                 for (int j = threadIdx.x; j < span; j += THREADS) {
                     if (mc.info_mask && !mc.info_mask[j]) continue;
                     const unsigned est = (prev[j] < 0.f) ? 0u : 1u;
-                    const unsigned sent = mc.codeword ? mc.codeword[j] : 0u;
+                    const unsigned sent = mc.codeword ? mc.codeword[f * mc.codeword_stride + j] : 0u;
                     errs += (est != sent);
                 }
 #pragma unroll

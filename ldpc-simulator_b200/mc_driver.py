@@ -107,7 +107,8 @@ class MonteCarloEngine:
         return cw if self.graph_name == "std" else self.edd.to_alist_order(cw)
 
     def launch(self, frames_local, speed, snr_db, counters, *, codeword=None, frame_offset=0):
-        """Enqueue ``frames_local`` frames on the current stream, accumulating into ``counters`` (cuda int64[5])."""
+        """Enqueue ``frames_local`` frames on the current stream, accumulating into ``counters`` (cuda int64[5]).
+        ``codeword``: cuda uint8 [n] (sent by every frame) or [frames_local, n] (one per frame) or None (all-zero)."""
         torch = self.torch
         if frames_local <= 0:
             return
@@ -115,22 +116,31 @@ class MonteCarloEngine:
         _native.check(_native.lib().ldpc_mc_run(
             self.graph.handle, self.dtype, int(frames_local), self.max_iterations, self.flags,
             float(speed), float(snr_db), self.quirk, self.seed, int(self.rank), int(frame_offset),
-            codeword.data_ptr() if codeword is not None else None, self._mask.data_ptr(), self.k,
+            codeword.data_ptr() if codeword is not None else None,
+            (self.n if codeword is not None and codeword.dim() == 2 else 0), self._mask.data_ptr(), self.k,
             counters.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream(self.device).cuda_stream))
 
     def run_point(self, snr_db, speed, *, frames=None, min_frame_errors=None, max_frames=None,
-                  interval_frames=None, random_codewords=True, rng=None) -> PointCounters:
+                  interval_frames=None, random_codewords="frame", rng=None) -> PointCounters:
         """Simulate one SNR point.
 
         ``frames``: exact total (reference behaviour: ``--blocks`` per point), or
         ``min_frame_errors`` / ``max_frames``: run whole intervals until the reduced counters
         show enough frame errors or the frame budget is spent.
+        ``random_codewords``: "frame" = a fresh random codeword per frame (device encoder, what the
+        reference does), "interval"/True = one random codeword per interval (host encode), False = all-zero.
         """
         torch = self.torch
         rng = rng or np.random.default_rng(self.seed ^ 0xC0DE)
 
         def launch(frames_local, counters, frame_offset):
-            cw_dev = torch.as_tensor(self.codeword(rng)).to(self.device) if random_codewords else None
+            cw_dev = None
+            if random_codewords == "frame" and frames_local > 0:
+                # a fresh random codeword per frame, drawn and encoded on the device (main.py:296-303)
+                cw_dev = self.edd.device_encoder(self.graph_name).encode(
+                    frames_local, seed=self.seed, stream_id=self.rank, frame_offset=frame_offset)
+            elif random_codewords:
+                cw_dev = torch.as_tensor(self.codeword(rng)).to(self.device)
             self.launch(frames_local, speed, snr_db, counters, codeword=cw_dev, frame_offset=frame_offset)
 
         with torch.cuda.device(self.device):
