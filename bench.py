@@ -96,6 +96,23 @@ class ClockSampler:
                 "power_w_max": max(power), "samples": len(sm)}
 
 
+def pin_to_gpu_numa_node(gpu_index):
+    """Bind this rank to the CPUs NVML reports as local to its GPU (multi-GPU end-to-end runs are limited by
+    host-memory locality of the pinned LLR buffers).  Best effort: silently skipped when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = {c for c in range(ncpu) if (mask[c // 64] >> (c % 64)) & 1} & allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def cpu_reference_run(frames, nthreads, seed=1):
     """Time the oracle port on `frames` frames of the bench workload; returns (info bit/s, seconds)."""
     from oracle import spa_oracle as so
@@ -113,7 +130,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0))
     from oracle import spa_oracle as so
     so.build()
     per_step = 192 * cores
@@ -227,6 +244,8 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    all_cpus = os.sched_getaffinity(0)
+    pin_to_gpu_numa_node(local_rank)      # pinned staging buffers are first-touched near the GPU's PCIe root
 
     import _native
     from channel import Channel
@@ -358,7 +377,8 @@ def main():
                 "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
     }
 
-    cores = os.cpu_count() or 1
+    os.sched_setaffinity(0, all_cpus)     # the CPU baseline may use every host core again
+    cores = len(all_cpus)
     cpu = None
     if world == 1:
         sample = args.cpu_frames or 2048 * cores
