@@ -65,6 +65,16 @@ typedef enum ldpc_dtype {
 #define LDPC_FLAG_FORCE_GENERIC 0x8u /* never pick the resident QC kernel */
 #define LDPC_FLAG_TABLE_KERNEL  0x10u /* resident path: use the table-driven kernel even when a kernel
                                          specialised at build time for this base matrix exists (tests) */
+#define LDPC_FLAG_NO_JIT        0x20u /* resident path: never specialise the kernel at run time (NVRTC);
+                                         unregistered base matrices then use the table-driven kernel */
+
+/* Which kernel family a (graph, dtype, flags) combination runs on (ldpc_graph_prepare). */
+typedef enum ldpc_kernel_kind {
+    LDPC_KERNEL_GENERIC = 0,       /* frame-minor streaming kernels, any graph */
+    LDPC_KERNEL_QC_TABLE = 1,      /* SM-resident, shift tables read at run time */
+    LDPC_KERNEL_QC_REGISTERED = 2, /* SM-resident, specialised when the library was built */
+    LDPC_KERNEL_QC_JIT = 3         /* SM-resident, specialised at run time with NVRTC */
+} ldpc_kernel_kind;
 
 typedef struct ldpc_graph ldpc_graph;
 
@@ -124,6 +134,24 @@ int ldpc_graph_info(const ldpc_graph* g, int* m, int* n, int64_t* nnz, int* max_
 
 /* Copies the detected shift table (capacity in entries); returns 1 if QC, 0 if not. */
 int ldpc_graph_qc_shifts(const ldpc_graph* g, int16_t* shift, int64_t shift_cap);
+
+/*
+ * Selects -- and, for LDPC_KERNEL_QC_JIT, compiles and loads -- the kernels ldpc_decode_batch /
+ * ldpc_mc_run will use for this graph, so that the first decode call does not pay for it.  Optional:
+ * the decode calls do the same lazily.  *kind (may be NULL) receives an ldpc_kernel_kind.  A base
+ * matrix that is not in the build-time registry is specialised with NVRTC (about 2 s once per code and
+ * machine; cubins are cached under $LDPC_JIT_CACHE, default ~/.cache/ldpc_b200; the NVRTC library is
+ * found through $LDPC_NVRTC_LIB, the loader path or /usr/local/cuda/lib64).
+ */
+int ldpc_graph_prepare(const ldpc_graph* g, int dtype, unsigned flags, int* kind);
+
+/*
+ * Host only (no device needed): the block-row schedule the specialised resident kernel uses for a base
+ * matrix, written as the C++ type text the kernel is instantiated with (type_text, may be NULL), and,
+ * when cubin_bytes is not NULL, a trial NVRTC compilation for sm_100a reporting the size of the cubin.
+ */
+int ldpc_host_jit_compile(int z, int mb, int nb, const int16_t* shift, char* type_text, size_t type_cap,
+                          size_t* cubin_bytes);
 
 void ldpc_graph_destroy(ldpc_graph* g);
 

@@ -14,12 +14,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", os.environ.get("LDPC_LIB_NAME", "libldpc_b200.so"))
 
 LDPC_F64, LDPC_F32, LDPC_F32_FAST = 0, 1, 2
-FLAG_EARLY_TERM, FLAG_COMPACT, FLAG_FIX_ODD_SIGN, FLAG_FORCE_GENERIC, FLAG_TABLE_KERNEL = 0x1, 0x2, 0x4, 0x8, 0x10
+FLAG_EARLY_TERM, FLAG_COMPACT, FLAG_FIX_ODD_SIGN, FLAG_FORCE_GENERIC, FLAG_TABLE_KERNEL, FLAG_NO_JIT = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
+KERNEL_KINDS = ("generic", "qc_table", "qc_registered", "qc_jit")      # ldpc_kernel_kind
 ABI_VERSION = 1
 
 EXPORTS = [
     "ldpc_host_edge_index", "ldpc_host_detect_qc", "ldpc_host_standard_form",
     "ldpc_graph_create_csr", "ldpc_graph_create_qc", "ldpc_graph_info", "ldpc_graph_qc_shifts",
+    "ldpc_graph_prepare", "ldpc_host_jit_compile",
     "ldpc_graph_destroy", "ldpc_workspace_bytes", "ldpc_decode_batch", "ldpc_decode_batch_host",
     "ldpc_mc_run", "ldpc_mc_workspace_bytes", "ldpc_channel_llr", "ldpc_encoder_create", "ldpc_encoder_destroy",
     "ldpc_encode_batch", "ldpc_kernel_launch_count",
@@ -65,6 +67,8 @@ def lib():
         "ldpc_graph_create_qc": (C.c_int, [C.c_int, C.c_int, C.c_int, i16p, C.POINTER(vp)]),
         "ldpc_graph_info": (C.c_int, [vp, ip, ip, C.POINTER(i64), ip, ip, ip, ip, ip]),
         "ldpc_graph_qc_shifts": (C.c_int, [vp, i16p, i64]),
+        "ldpc_graph_prepare": (C.c_int, [vp, C.c_int, C.c_uint, ip]),
+        "ldpc_host_jit_compile": (C.c_int, [C.c_int, C.c_int, C.c_int, i16p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
         "ldpc_graph_destroy": (None, [vp]),
         "ldpc_workspace_bytes": (C.c_size_t, [vp, i64, C.c_int]),
         "ldpc_decode_batch": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_uint, vp, vp, vp, vp, vp, vp, C.c_int,

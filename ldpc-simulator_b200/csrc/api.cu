@@ -13,7 +13,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 bool use_resident(const ldpc_graph* g, int dtype, unsigned flags)
 {
-    return dtype == LDPC_F32_FAST && !(flags & LDPC_FLAG_FORCE_GENERIC) && qc_resident_supported(g);
+    return dtype == LDPC_F32_FAST && !(flags & LDPC_FLAG_FORCE_GENERIC) && qc_resident_kind(g, flags) != LDPC_KERNEL_GENERIC;
 }
 
 int check_common(const ldpc_graph* g, int dtype, int64_t frames, int max_iter)
@@ -99,7 +99,7 @@ int decode_device(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, 
         return qc_resident_decode(g, frames, max_iter, flags, (const float*)llr, z, zbits, conv, ok,
                                   (float*)post, mc, ws, ws_bytes, stream);
     }
-    if (dtype == LDPC_F32_FAST && !(flags & LDPC_FLAG_FORCE_GENERIC) && !norm && !qc_resident_supported(g)) {
+    if (dtype == LDPC_F32_FAST && !(flags & LDPC_FLAG_FORCE_GENERIC) && !norm) {
         set_error("LDPC_F32_FAST needs a quasi-cyclic graph supported by the resident kernel; "
                   "use LDPC_F32 (or LDPC_FLAG_FORCE_GENERIC) for this graph");
         return LDPC_ERR_UNSUPPORTED;
@@ -145,8 +145,20 @@ __global__ void __launch_bounds__(256) k_mufu_peak(float* sink, int iters)
 extern "C" size_t ldpc_workspace_bytes(const ldpc_graph* g, int64_t frames, int dtype)
 {
     if (!g || frames < 0) return 0;
-    if (dtype == LDPC_F32_FAST && qc_resident_supported(g)) return 256;
+    if (dtype == LDPC_F32_FAST && qc_resident_kind(g, 0) != LDPC_KERNEL_GENERIC) return 256;
     return generic_workspace_bytes(g, std::max<int64_t>(frames, 1), dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32);
+}
+
+extern "C" int ldpc_graph_prepare(const ldpc_graph* g, int dtype, unsigned flags, int* kind)
+{
+    if (!g) { set_error("null graph"); return LDPC_ERR_INVALID; }
+    int k = use_resident(g, dtype, flags) ? qc_resident_kind(g, flags) : LDPC_KERNEL_GENERIC;
+    if (k == LDPC_KERNEL_QC_JIT && qc_jit_prepare(g) != LDPC_OK) {
+        if (!qc_resident_supported(g)) return LDPC_ERR_UNSUPPORTED;     // message set by qc_jit_prepare
+        k = LDPC_KERNEL_QC_TABLE;
+    }
+    if (kind) *kind = k;
+    return LDPC_OK;
 }
 
 extern "C" int ldpc_decode_batch(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
@@ -283,7 +295,7 @@ extern "C" int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t fr
 extern "C" size_t ldpc_mc_workspace_bytes(const ldpc_graph* g, int64_t frames, int dtype)
 {
     if (!g || frames < 0) return 0;
-    if (dtype == LDPC_F32_FAST && qc_resident_supported(g)) return 256;
+    if (dtype == LDPC_F32_FAST && qc_resident_kind(g, 0) != LDPC_KERNEL_GENERIC) return 256;
     const size_t esz = dtype == LDPC_F64 ? 8 : 4;
     const int64_t F = std::max<int64_t>(frames, 1);
     return align_up((size_t)F * g->n * esz, 256) + align_up((size_t)F * g->n, 256) + align_up((size_t)F * 4, 256) +

@@ -15,7 +15,7 @@
 // All arithmetic uses explicit _rn intrinsics so that the standalone channel
 // kernel and the copy inlined into the resident decoder produce identical bits.
 #pragma once
-#include <stdint.h>
+#include "qc_device.cuh"
 
 namespace ldpc {
 

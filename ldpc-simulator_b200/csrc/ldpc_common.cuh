@@ -12,6 +12,7 @@
 #include <atomic>
 
 #include "../../include/ldpc_b200.h"
+#include "qc_device.cuh"
 
 namespace ldpc {
 
@@ -86,20 +87,7 @@ int generic_decode(const ldpc_graph* g, int dtype, int64_t frames, int max_iter,
                    cudaStream_t stream);
 
 // ---- resident quasi-cyclic path, spa_qc_resident.cu ------------------------
-struct McParams {               // in-kernel channel (awgn_philox.cuh); enabled when active
-    bool active = false;
-    float noise_dev = 1.f;      // sigma^2 (reference quirk, channel.py:68) or sigma
-    float llr_scale = 2.f;      // 2 / sigma^2 (channel.py:80)
-    uint64_t seed = 0;
-    uint32_t stream_id = 0;
-    uint64_t frame_offset = 0;
-    const uint8_t* codeword = nullptr;       // device, [n] (or [frames][n]) or null = all-zero
-    long long codeword_stride = 0;           // bytes between the codewords of consecutive frames, 0 = one for all
-    const uint8_t* info_mask = nullptr;      // device, [n] or null = first k_info positions
-    int k_info = 0;
-    unsigned long long* counters = nullptr;  // device uint64[5]
-};
-bool qc_resident_supported(const ldpc_graph* g);
+bool qc_resident_supported(const ldpc_graph* g);   // by the table-driven kernel
 int qc_resident_decode(const ldpc_graph* g, int64_t frames, int max_iter, unsigned flags,
                        const float* llr_dev, uint8_t* z_dev, uint32_t* zbits_dev, int32_t* conv_dev,
                        uint8_t* ok_dev, float* post_dev, const McParams& mc, void* ws, size_t ws_bytes,
@@ -110,6 +98,15 @@ int qc_spec_find(const ldpc_graph* g);   // registry index or -1
 int qc_spec_decode(int idx, const ldpc_graph* g, int64_t frames, int max_iter, unsigned flags,
                    const float* llr_dev, uint8_t* z_dev, uint32_t* zbits_dev, int32_t* conv_dev,
                    uint8_t* ok_dev, float* post_dev, const McParams& mc, void* ws, cudaStream_t stream);
+
+// run-time specialised kernels for any other base matrix (NVRTC), qc_jit.cu
+bool qc_jit_supported(const ldpc_graph* g);
+int qc_jit_prepare(const ldpc_graph* g);
+int qc_jit_decode(const ldpc_graph* g, int64_t frames, int max_iter, unsigned flags,
+                  const float* llr_dev, uint8_t* z_dev, uint32_t* zbits_dev, int32_t* conv_dev,
+                  uint8_t* ok_dev, float* post_dev, const McParams& mc, void* ws, cudaStream_t stream);
+// kernel family of the resident path for (g, flags): an ldpc_kernel_kind, LDPC_KERNEL_GENERIC if none
+int qc_resident_kind(const ldpc_graph* g, unsigned flags);
 
 // ---- channel / counters, mc.cu ---------------------------------------------
 int channel_fill(int n, int dtype, int64_t frames, double speed, double snr_db, int quirk, uint64_t seed,

@@ -419,14 +419,18 @@ int qc_resident_decode(const ldpc_graph* g, int64_t frames, int max_iter, unsign
                        uint8_t* ok_dev, float* post_dev, const McParams& mc, void* ws, size_t ws_bytes,
                        cudaStream_t stream)
 {
-    if (!qc_resident_supported(g)) { set_error("graph is not supported by the resident QC kernel"); return LDPC_ERR_UNSUPPORTED; }
+    const int kind = qc_resident_kind(g, flags);
+    if (kind == LDPC_KERNEL_GENERIC) { set_error("graph is not supported by the resident QC kernels"); return LDPC_ERR_UNSUPPORTED; }
     if (frames == 0) return LDPC_OK;
     if (ws && ws_bytes < 256) ws = nullptr;
-    if (!(flags & LDPC_FLAG_TABLE_KERNEL)) {
-        const int spec = qc_spec_find(g);
-        if (spec >= 0)
-            return qc_spec_decode(spec, g, frames, max_iter, flags, llr_dev, z_dev, zbits_dev, conv_dev, ok_dev,
-                                  post_dev, mc, ws, stream);
+    if (kind == LDPC_KERNEL_QC_REGISTERED)
+        return qc_spec_decode(qc_spec_find(g), g, frames, max_iter, flags, llr_dev, z_dev, zbits_dev, conv_dev, ok_dev,
+                              post_dev, mc, ws, stream);
+    if (kind == LDPC_KERNEL_QC_JIT) {
+        const int rc = qc_jit_decode(g, frames, max_iter, flags, llr_dev, z_dev, zbits_dev, conv_dev, ok_dev, post_dev,
+                                     mc, ws, stream);
+        // a failed specialisation (remembered per code) leaves the table-driven kernel where it applies
+        if (rc != LDPC_ERR_UNSUPPORTED || !qc_resident_supported(g)) return rc;
     }
     Outputs out{z_dev, zbits_dev, conv_dev, ok_dev, post_dev};
     switch (pick_shape(g)) {
@@ -437,6 +441,16 @@ int qc_resident_decode(const ldpc_graph* g, int64_t frames, int max_iter, unsign
     }
     set_error("no resident kernel shape for this graph");
     return LDPC_ERR_UNSUPPORTED;
+}
+
+int qc_resident_kind(const ldpc_graph* g, unsigned flags)
+{
+    if (!g || !g->is_qc) return LDPC_KERNEL_GENERIC;
+    const bool table = qc_resident_supported(g);
+    if (flags & LDPC_FLAG_TABLE_KERNEL) return table ? LDPC_KERNEL_QC_TABLE : LDPC_KERNEL_GENERIC;
+    if (qc_spec_find(g) >= 0) return LDPC_KERNEL_QC_REGISTERED;
+    if (!(flags & LDPC_FLAG_NO_JIT) && qc_jit_supported(g)) return LDPC_KERNEL_QC_JIT;
+    return table ? LDPC_KERNEL_QC_TABLE : LDPC_KERNEL_GENERIC;
 }
 
 void qc_resident_release(ldpc_graph* g)

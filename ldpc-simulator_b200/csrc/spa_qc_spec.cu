@@ -2,6 +2,7 @@
 // for the base matrices listed in qc_registry.json.  A graph whose (z, mb, nb, shift table)
 // matches an entry exactly runs the specialised kernel; any other quasi-cyclic graph falls
 // back to the table-driven kernel in spa_qc_resident.cu.
+#include "ldpc_common.cuh"
 #include "qc_codes_gen.cuh"
 
 #include <algorithm>
@@ -51,15 +52,8 @@ template <class C>
 int launch_code(C code, const Args& a)
 {
     const bool early = (a.flags & LDPC_FLAG_EARLY_TERM) != 0;
-    constexpr int TZ = (C::Z + 31) / 32 * 32;
-    constexpr int T = TZ * C::TEAMS;                 // CTA = teams x ceil32(z) threads
-    // CTAs per SM the register budget is sized for.  Measured on B200 (profiles/r1_tuning.md): the
-    // kernel is bound by instruction issue and the MUFU pipe, not by latency, so a spill-free build
-    // with 12 warps per SM beats a 24-warp build that spills; 168 registers per thread hold the
-    // messages, the hoisted rotated addresses and the working set of one check row.
-    constexpr int NEED = 2 * C::MAXSLOT + 60;
-    constexpr int B0 = 65536 / (T * (NEED > 168 ? 255 : 168));
-    constexpr int B = B0 < 1 ? 1 : (B0 > 32 ? 32 : B0);
+    constexpr int T = qc::LaunchShape<C>::THREADS;
+    constexpr int B = qc::LaunchShape<C>::MINB;
     return early ? launch_spec<C, true, T, B>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream)
                  : launch_spec<C, false, T, B>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream);
 }

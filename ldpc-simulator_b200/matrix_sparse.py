@@ -60,6 +60,14 @@ class DeviceGraph:
         _native.check(_native.lib().ldpc_graph_qc_shifts(self.handle, out.ctypes.data_as(C.POINTER(C.c_int16)), out.size))
         return out.reshape(self.qc_mb, self.qc_nb)
 
+    def prepare(self, precision="f32_fast", flags=0) -> str:
+        """Select (and, for an unregistered quasi-cyclic base matrix, compile with NVRTC and load) the
+        kernels a decode with this precision / flags will run; returns the kernel family name."""
+        dt = {"f64": _native.LDPC_F64, "f32": _native.LDPC_F32, "f32_fast": _native.LDPC_F32_FAST}[precision]
+        kind = C.c_int(0)
+        _native.check(_native.lib().ldpc_graph_prepare(self.handle, dt, int(flags), C.byref(kind)))
+        return _native.KERNEL_KINDS[kind.value]
+
     def close(self):
         if self._h is not None:
             _native.lib().ldpc_graph_destroy(self._h)

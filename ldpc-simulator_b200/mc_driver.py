@@ -64,7 +64,8 @@ def split_frames(total, rank, world):
 
 class MonteCarloEngine:
     def __init__(self, edd, *, graph="std", precision="f64", max_iterations=20, early_termination=True,
-                 fix_odd_check_sign=False, sigma_sq_quirk=True, seed=0x5EED, device=None, group=None):
+                 fix_odd_check_sign=False, sigma_sq_quirk=True, seed=0x5EED, device=None, group=None,
+                 kernel_flags=0):
         import torch
         self.torch = torch
         self.edd = edd
@@ -73,7 +74,7 @@ class MonteCarloEngine:
         self.dtype = _PRECISIONS[precision]
         self.max_iterations = int(max_iterations)
         self.flags = (_native.FLAG_EARLY_TERM if early_termination else 0) | \
-                     (_native.FLAG_FIX_ODD_SIGN if fix_odd_check_sign else 0)
+                     (_native.FLAG_FIX_ODD_SIGN if fix_odd_check_sign else 0) | int(kernel_flags)
         self.quirk = int(bool(sigma_sq_quirk))
         self.seed = int(seed)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -84,6 +85,8 @@ class MonteCarloEngine:
         self.world = dist.get_world_size(group) if self.distributed else 1
         with torch.cuda.device(self.device):
             self.graph = edd.device_graph(graph)
+            # compile / load now (NVRTC for an unregistered quasi-cyclic base matrix), not in the first interval
+            self.kernel = self.graph.prepare(precision, self.flags)
         self.k = int(edd._k)
         self.n = int(edd._n)
         self._mask = torch.as_tensor(edd.info_mask(graph)).to(self.device)

@@ -107,7 +107,7 @@ class SPA_Decoder:
             raise ValueError(f"unknown precision {name!r}")
         return name, _PRECISIONS[name]
 
-    def _flags(self, early_termination=None, compact=False, table_kernel=False):
+    def _flags(self, early_termination=None, compact=False, table_kernel=False, jit=True):
         s = self.m_pSettings
         early = getattr(s, "is_early_termination", lambda: True)() if early_termination is None else early_termination
         flags = _native.FLAG_EARLY_TERM if early else 0
@@ -115,6 +115,8 @@ class SPA_Decoder:
             flags |= _native.FLAG_COMPACT
         if table_kernel:
             flags |= _native.FLAG_TABLE_KERNEL
+        if not jit:
+            flags |= _native.FLAG_NO_JIT
         if getattr(s, "is_fix_odd_check_sign", lambda: False)():
             flags |= _native.FLAG_FIX_ODD_SIGN
         return flags
@@ -122,8 +124,11 @@ class SPA_Decoder:
     # ---- batched decode, host buffers (the end-to-end call) -------------------------
     def decode_batch(self, llr, *, precision=None, early_termination=None, compact=False, want_z=True,
                      want_bits=False, want_posterior=False, normalized_llr=None, max_iterations=None,
-                     table_kernel=False):
+                     table_kernel=False, jit=True):
         """Decode F frames given as a host array ``llr`` [F, n] (numpy, or a pinned CPU torch tensor).
+
+        ``table_kernel`` / ``jit=False`` pick the table-driven resident kernel instead of the one
+        specialised for the base matrix (at build time, or with NVRTC at run time); for tests.
 
         Returns a ``BatchResult`` of host numpy arrays.  Host<->device copies are pipelined inside
         ``ldpc_decode_batch_host`` (pinned staging, several streams).
@@ -163,14 +168,15 @@ class SPA_Decoder:
         k_info = int(self.m_pData._n - self.m_pData._m) if calc_norm else 0
         ptr = lambda a: a.ctypes.data if a is not None else None
         _native.check(_native.lib().ldpc_decode_batch_host(
-            g.handle, dtype, frames, int(max_it), self._flags(early_termination, compact, table_kernel), in_ptr,
+            g.handle, dtype, frames, int(max_it), self._flags(early_termination, compact, table_kernel, jit), in_ptr,
             ptr(z), ptr(zbits), ptr(conv), ptr(ok), ptr(post), ptr(norm), k_info))
         del keep
         return BatchResult(z, zbits, ok, conv, post, norm)
 
     # ---- batched decode, device tensors (async on the current stream) ---------------
     def decode_batch_device(self, llr, *, precision=None, early_termination=None, compact=False,
-                            want_posterior=False, normalized_llr=False, max_iterations=None, workspace=None):
+                            want_posterior=False, normalized_llr=False, max_iterations=None, workspace=None,
+                            table_kernel=False, jit=True, force_generic=False):
         """``llr``: CUDA tensor [F, n] (float64 for 'f64', float32 otherwise).  Returns CUDA tensors."""
         import torch
         g = self.graph
@@ -195,7 +201,9 @@ class SPA_Decoder:
             workspace = torch.empty(need, dtype=torch.uint8, device=dev)
         dp = lambda t: t.data_ptr() if t is not None else None
         _native.check(_native.lib().ldpc_decode_batch(
-            g.handle, dtype, frames, int(max_it), self._flags(early_termination, compact), llr.data_ptr(),
+            g.handle, dtype, frames, int(max_it),
+            self._flags(early_termination, compact, table_kernel, jit) | (_native.FLAG_FORCE_GENERIC if force_generic else 0),
+            llr.data_ptr(),
             z.data_ptr(), conv.data_ptr(), ok.data_ptr(), dp(post), dp(norm),
             int(self.m_pData._n - self.m_pData._m), workspace.data_ptr(), workspace.numel(),
             torch.cuda.current_stream(dev).cuda_stream))

@@ -54,6 +54,7 @@ CODE_FILES = {
     "tanner_155_64": "Custom LDPC Codes/Tanner_155_64.alist.txt",
     "wifi_648_r083": "Standardized LDPC Codes/wifi_648_r083.alist.txt",
     "wimax_576_0.5": "Wimax LDPC Codes/wimax_576_0.5.alist.txt",
+    "wimax_1152_0.66B": "Wimax LDPC Codes/wimax_1152_0.66B.alist.txt",
     "wimax_2304_0.5": "Wimax LDPC Codes/wimax_2304_0.5.alist.txt",
     "wimax_2304_0.75B": "Wimax LDPC Codes/wimax_2304_0.75B.alist.txt",
     "wimax_2304_0.83": "Wimax LDPC Codes/wimax_2304_0.83.alist.txt",

@@ -63,3 +63,56 @@ def test_no_cpu_fallback_without_a_device():
     with pytest.raises(_native.LdpcError) as e:
         DeviceGraph.from_csr(h)
     assert e.value.code == -2
+
+
+# ---- run-time specialisation (csrc/qc_jit.cu): host side, no GPU needed ---------------------------
+def _jit(z, shift, compile_it=False):
+    lib = _native.lib()
+    sh = np.ascontiguousarray(shift, dtype=np.int16)
+    text = C.create_string_buffer(1 << 16)
+    size = C.c_size_t(0)
+    rc = lib.ldpc_host_jit_compile(int(z), sh.shape[0], sh.shape[1], sh.ctypes.data_as(C.POINTER(C.c_int16)),
+                                   text, len(text), C.byref(size) if compile_it else None)
+    return rc, text.value.decode(), size.value
+
+
+def test_run_time_schedule_equals_the_build_time_generator():
+    """qc_jit.cu re-implements build_native.schedule_rows in C++: for the registered codes it must
+    write exactly the Code<...> type the build generated into qc_codes_gen.cuh."""
+    import json
+    csrc = os.path.join(REPO, "ldpc-simulator_b200", "csrc")
+    gen = open(os.path.join(csrc, "qc_codes_gen.cuh")).read()
+    for code in json.load(open(os.path.join(csrc, "qc_registry.json"))):
+        rc, text, _ = _jit(code["z"], np.array(code["shift"]))
+        assert rc == 0
+        ident = "Code_" + "".join(ch if ch.isalnum() else "_" for ch in code["name"])
+        built = re.search(r"using %s = (Code<.*?>);\nstatic" % ident, gen, re.S).group(1)
+        assert re.sub(r"\s", "", built) == re.sub(r"\s", "", text), code["name"]
+
+
+def test_nvrtc_specialises_an_unregistered_code_for_sm_100a(tmp_path, monkeypatch):
+    """wimax_1152_0.66B (z=48, 8x24 base, check degree 10/11) is in neither the registry nor the shapes
+    of the table-driven kernel.  NVRTC cross-compiles without a device; the cubin lands in the cache."""
+    from conftest import load_code
+    z, shift = load_code("wimax_1152_0.66B").sparse_matrix().detect_qc()
+    assert (z, shift.shape) == (48, (8, 24))
+    monkeypatch.setenv("LDPC_JIT_CACHE", str(tmp_path))
+    rc, text, size = _jit(z, shift, compile_it=True)
+    if rc != 0 and b"libnvrtc not found" in _native.lib().ldpc_last_error():
+        pytest.skip("no NVRTC on this machine")
+    assert rc == 0, _native.lib().ldpc_last_error()
+    assert text.startswith("Code<48, 1152,") and size > 100_000
+    cached = [f for f in os.listdir(tmp_path) if f.endswith(".cubin")]
+    assert len(cached) == 1 and os.path.getsize(tmp_path / cached[0]) == size
+    head = open(tmp_path / cached[0], "rb").read(4)
+    assert head == b"\x7fELF"
+    rc2, _, size2 = _jit(z, shift, compile_it=True)          # second call: served from the disk cache
+    assert rc2 == 0 and size2 == size
+
+
+def test_jit_rejects_what_the_kernel_cannot_run():
+    lib = _native.lib()
+    rc, _, _ = _jit(8, np.array([[0, 9]]))                    # shift >= z
+    assert rc == -1 and b"out of range" in lib.ldpc_last_error()
+    rc, _, _ = _jit(8, np.array([[0, -1], [1, -1]]), compile_it=True)     # degree-1 checks, empty column block
+    assert rc == -4

@@ -275,6 +275,43 @@ def test_specialised_and_table_driven_resident_kernels_agree(name):
             assert (tab.z == ref["z"]).mean() > 0.999 and (tab.ok == ref["ok"]).mean() > 0.98
 
 
+@pytest.mark.parametrize("name,table", [("wifi_648_r083", True), ("tanner_155_64", True), ("wimax_1152_0.66B", False)])
+def test_run_time_specialised_kernel(name, table):
+    """A quasi-cyclic base matrix outside csrc/qc_registry.json gets the resident kernel specialised at run
+    time (csrc/qc_jit.cu: NVRTC -> cubin -> driver launch).  One launch per chunk; results against the
+    oracle, the generic fp32 kernels and, where its shapes apply, the table-driven kernel (which
+    LDPC_FLAG_NO_JIT selects).  wimax_1152_0.66B (8 block rows of degree 10/11) has no table shape: without
+    the specialisation LDPC_F32_FAST refuses the graph."""
+    import _native
+    code = load_code(name)
+    dec = make_decoder(code, 12, "f32_fast")
+    assert dec.graph.prepare("f32_fast") == "qc_jit"
+    assert dec.graph.prepare("f32_fast", _native.FLAG_NO_JIT) == ("qc_table" if table else "generic")
+    assert dec.graph.prepare("f64") == "generic"
+    rng = np.random.default_rng(23)
+    llr = awgn_llr(rng, 512, code.n, np.resize(np.array([2.0, 4.0, 6.0]), 512)).astype(np.float32)
+    ref = oracle(code, llr.astype(np.float64), 12)
+    gen = make_decoder(code, 12, "f32").decode_batch(llr, want_posterior=True)
+    for early in (True, False):
+        before = _native.launches()
+        jit = dec.decode_batch(llr, want_posterior=True, early_termination=early)
+        assert _native.launches() - before == 1
+        if early:
+            assert (jit.z == ref["z"]).mean() > 0.999 and (jit.ok == ref["ok"]).mean() > 0.98
+            assert (jit.z == gen.z).mean() > 0.999 and (jit.ok == gen.ok).mean() > 0.98
+            both = (jit.ok == 1) & (ref["ok"] == 1)
+            assert (jit.conv_it[both] == ref["conv_it"][both]).mean() > 0.97
+            close = np.isclose(jit.post, gen.post, rtol=5e-3, atol=5e-3).all(axis=1)
+            assert close[jit.conv_it == gen.conv_it].mean() > 0.98
+        if table:
+            tab = dec.decode_batch(llr, want_posterior=True, early_termination=early, jit=False)
+            assert (tab.z == jit.z).mean() > 0.9999 and (tab.conv_it == jit.conv_it).mean() > 0.99
+            np.testing.assert_allclose(jit.post, tab.post, rtol=2e-3, atol=2e-3)
+        else:
+            with pytest.raises(_native.LdpcError):
+                dec.decode_batch(llr, jit=False)
+
+
 def test_early_termination_on_large_codes():
     """Config 3.  Frames leave the active set as soon as their syndrome vanishes (dynamic frame queue in
     the resident kernel, active-list compaction in the generic kernels); per-frame results must equal the
