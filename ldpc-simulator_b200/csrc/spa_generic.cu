@@ -12,17 +12,25 @@
 //   var node     M_ij = L_j - E_ij                               (:260-268)
 //
 // Data layout in HBM (one chunk of Fc frames, Fc a multiple of 32):
-//   lch  [n][Fc]    channel LLRs, frame-minor
-//   M    [nnz][Fc]  variable->check messages, edge-major (CSR edge order)
-//   E    [nnz][Fc]  check->variable messages
-//   post [n][Fc]    posteriors of the last executed pass
-//   zb   [n][Fc]    hard decisions (uint8)
+//   lch  [n][Fc]       channel LLRs, frame-minor
+//   E    [2][nnz][Fc]  check->variable messages of the previous / the current pass,
+//                      edge-major (CSR edge order)
+//   post [n][Fc]       posteriors of the last executed pass
+//   zb   [n][Fc]       hard decisions (uint8)
 // so that a warp = 32 consecutive frames of one node and every access is a
 // coalesced 128/256-byte row segment.  Frames that have converged are dropped
 // from the active list (LDPC_FLAG_COMPACT) or masked (default).
 //
-// The kernels are HBM-streaming by construction (per pass and frame: read M,
-// write E, read E, write M, plus O(n) vectors); DESIGN.md gives the roofline.
+// The variable->check messages are never stored: the check-node pass forms
+// M_ij = L_j - E_ij (:260-268) from the posterior and the message of the previous
+// pass -- the same subtraction on the same operands, so results are unchanged --
+// which removes one message sweep in each direction.  Work is ordered frame block
+// major (consecutive warps = consecutive nodes of the SAME 32 frames): the
+// posterior words a check gathers were written / are re-read by warps that run at
+// about the same time and come from L2, not HBM.
+//
+// The kernels are HBM-streaming by construction (per pass and frame: read E,
+// write E, read E, plus O(n) vectors); DESIGN.md gives the roofline.
 #include "ldpc_common.cuh"
 
 namespace ldpc {
@@ -126,25 +134,59 @@ __global__ void k_init_chunk(ChunkState st, int Fc, int64_t valid)
     }
 }
 
+// Frame-block-major walk over (node, 32-frame block) pairs: warp w of the grid starts at pair w and
+// advances by the number of warps in the grid, without a 64-bit division per item.
+struct PairWalk {
+    int node, tb, nodes, nblk, dq, dr;
+    __device__ __forceinline__ PairWalk(int nodes_, int cpad)
+    {
+        nodes = nodes_;
+        nblk = cpad >> 5;
+        const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        const unsigned stride = (gridDim.x * blockDim.x) >> 5;
+        tb = (int)(warp / (unsigned)nodes);
+        node = (int)(warp - (unsigned)tb * (unsigned)nodes);
+        dq = (int)(stride / (unsigned)nodes);
+        dr = (int)(stride - (unsigned)dq * (unsigned)nodes);
+    }
+    __device__ __forceinline__ bool valid() const { return tb < nblk; }
+    __device__ __forceinline__ void next()
+    {
+        tb += dq;
+        node += dr;
+        if (node >= nodes) { node -= nodes; ++tb; }
+    }
+};
+
+// Variable->check message of edge e (column j) for frame slot f: the channel value in the first pass
+// (:88-96), afterwards posterior minus the check's own previous message (:260-268).
+template <typename T>
+__device__ __forceinline__ T v2c_message(const T* __restrict__ lch, const T* __restrict__ post,
+                                         const T* __restrict__ Eold, int j, int e, int Fc, int f, int first_pass)
+{
+    if (first_pass) return lch[(size_t)j * Fc + f];
+    return post[(size_t)j * Fc + f] - Eold[(size_t)e * Fc + f];
+}
+
 // Check-node pass.  One thread = (check i, frame slot t); a warp covers 32
 // consecutive slots of one check, so the degree loop is warp-uniform.
 // MAXD > 0: tanh values are kept in registers (degree <= MAXD);
-// MAXD == 0: two sweeps over the row, tanh recomputed in the second.
+// MAXD == 0: two sweeps over the row, tanh values parked in the output slots in between.
 template <typename T, int MAXD>
 __global__ void __launch_bounds__(kThreads)
 k_check_nodes(int m, const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
-              const T* __restrict__ lch, T* __restrict__ M, T* __restrict__ E, int Fc,
+              const T* __restrict__ lch, const T* __restrict__ post, const T* __restrict__ Eold,
+              T* __restrict__ E, int Fc,
               const int32_t* __restrict__ active, const int32_t* __restrict__ count_ptr,
               const uint8_t* __restrict__ done, int first_pass, int fix_odd)
 {
     const int count = *count_ptr;
     if (count <= 0) return;
     const int cpad = (count + 31) & ~31;
-    const int64_t items = (int64_t)m * cpad;
-    for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < items;
-         id += (int64_t)gridDim.x * blockDim.x) {
-        const int i = (int)(id / cpad);
-        const int t = (int)(id - (int64_t)i * cpad);
+    const int lane = threadIdx.x & 31;
+    for (PairWalk pw(m, cpad); pw.valid(); pw.next()) {          // frame block major: see the header
+        const int i = pw.node;
+        const int t = pw.tb * 32 + lane;
         if (t >= count) continue;
         const int f = active[t];
         if (done[f]) continue;
@@ -156,9 +198,7 @@ k_check_nodes(int m, const int32_t* __restrict__ row_ptr, const int32_t* __restr
 #pragma unroll
             for (int q = 0; q < MAXD; ++q) {
                 if (q < d) {
-                    const T msg = first_pass ? lch[(size_t)col_idx[a + q] * Fc + f]
-                                             : M[(size_t)(a + q) * Fc + f];
-                    tv[q] = tanh_half_clipped<T>(msg);
+                    tv[q] = tanh_half_clipped<T>(v2c_message<T>(lch, post, Eold, col_idx[a + q], a + q, Fc, f, first_pass));
                     total *= tv[q];
                 }
             }
@@ -180,15 +220,15 @@ k_check_nodes(int m, const int32_t* __restrict__ row_ptr, const int32_t* __restr
                 }
             }
         } else {
+            // first sweep: park tanh(M/2) in this pass' message slot (E is double buffered, so the
+            // previous messages stay intact); second sweep: read it back, divide, atanh, overwrite.
             for (int q = 0; q < d; ++q) {
-                const T msg = first_pass ? lch[(size_t)col_idx[a + q] * Fc + f]
-                                         : M[(size_t)(a + q) * Fc + f];
-                total *= tanh_half_clipped<T>(msg);
+                const T tq = tanh_half_clipped<T>(v2c_message<T>(lch, post, Eold, col_idx[a + q], a + q, Fc, f, first_pass));
+                E[(size_t)(a + q) * Fc + f] = tq;
+                total *= tq;
             }
             for (int q = 0; q < d; ++q) {
-                const T msg = first_pass ? lch[(size_t)col_idx[a + q] * Fc + f]
-                                         : M[(size_t)(a + q) * Fc + f];
-                const T tq = tanh_half_clipped<T>(msg);
+                const T tq = E[(size_t)(a + q) * Fc + f];
                 T r;
                 if (Num<T>::abs_(tq) > Num<T>::small_tanh()) {
                     r = total / tq;
@@ -196,9 +236,7 @@ k_check_nodes(int m, const int32_t* __restrict__ row_ptr, const int32_t* __restr
                     r = T(1);
                     for (int u = 0; u < d; ++u) {
                         if (u == q) continue;
-                        const T mu = first_pass ? lch[(size_t)col_idx[a + u] * Fc + f]
-                                                : M[(size_t)(a + u) * Fc + f];
-                        r *= tanh_half_clipped<T>(mu);
+                        r *= tanh_half_clipped<T>(v2c_message<T>(lch, post, Eold, col_idx[a + u], a + u, Fc, f, first_pass));
                     }
                 }
                 T e = T(2) * Num<T>::atanh_(clip_unit<T>(r));
@@ -209,12 +247,13 @@ k_check_nodes(int m, const int32_t* __restrict__ row_ptr, const int32_t* __restr
     }
 }
 
-// Posterior + hard decision + variable-node pass (+ optional "normalized LLR"
-// sign-change count over the first k_info bits, spa_decoder.py:210-228).
+// Posterior + hard decision (+ optional "normalized LLR" sign-change count over the
+// first k_info bits, spa_decoder.py:210-228).  The variable->check messages of
+// :260-268 are formed by the next check-node pass (v2c_message).
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_var_nodes(int n, const int32_t* __restrict__ col_ptr, const int32_t* __restrict__ csc_edge,
-            const T* __restrict__ lch, T* __restrict__ M, const T* __restrict__ E,
+            const T* __restrict__ lch, const T* __restrict__ E,
             T* __restrict__ post, uint8_t* __restrict__ zb, int Fc,
             const int32_t* __restrict__ active, const int32_t* __restrict__ count_ptr,
             const uint8_t* __restrict__ done, int first_pass, int k_norm, int32_t* __restrict__ norm_cnt)
@@ -222,11 +261,10 @@ k_var_nodes(int n, const int32_t* __restrict__ col_ptr, const int32_t* __restric
     const int count = *count_ptr;
     if (count <= 0) return;
     const int cpad = (count + 31) & ~31;
-    const int64_t items = (int64_t)n * cpad;
-    for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < items;
-         id += (int64_t)gridDim.x * blockDim.x) {
-        const int j = (int)(id / cpad);
-        const int t = (int)(id - (int64_t)j * cpad);
+    const int lane = threadIdx.x & 31;
+    for (PairWalk pw(n, cpad); pw.valid(); pw.next()) {
+        const int j = pw.node;
+        const int t = pw.tb * 32 + lane;
         if (t >= count) continue;
         const int f = active[t];
         if (done[f]) continue;
@@ -241,10 +279,6 @@ k_var_nodes(int n, const int32_t* __restrict__ col_ptr, const int32_t* __restric
         }
         post[(size_t)j * Fc + f] = L;
         zb[(size_t)j * Fc + f] = (uint8_t)(L < T(0));             // :188
-        for (int q = a; q < b; ++q) {                             // :260-268
-            const size_t e = (size_t)csc_edge[q] * Fc + f;
-            M[e] = L - E[e];
-        }
     }
 }
 
@@ -258,11 +292,10 @@ k_syndrome(int m, const int32_t* __restrict__ row_ptr, const int32_t* __restrict
     const int count = *count_ptr;
     if (count <= 0) return;
     const int cpad = (count + 31) & ~31;
-    const int64_t items = (int64_t)m * cpad;
-    for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < items;
-         id += (int64_t)gridDim.x * blockDim.x) {
-        const int i = (int)(id / cpad);
-        const int t = (int)(id - (int64_t)i * cpad);
+    const int lane = threadIdx.x & 31;
+    for (PairWalk pw(m, cpad); pw.valid(); pw.next()) {
+        const int i = pw.node;
+        const int t = pw.tb * 32 + lane;
         if (t >= count) continue;
         const int f = active[t];
         if (done[f]) continue;
@@ -361,7 +394,7 @@ size_t bytes_per_chunk(const ldpc_graph* g, int64_t Fc)
 {
     size_t b = 0;
     b += align_up(sizeof(T) * (size_t)g->n * Fc, 256);        // lch
-    b += align_up(sizeof(T) * (size_t)g->nnz * Fc, 256) * 2;  // M, E
+    b += align_up(sizeof(T) * (size_t)g->nnz * Fc, 256) * 2;  // E of the previous / current pass
     b += align_up(sizeof(T) * (size_t)g->n * Fc, 256);        // post
     b += align_up((size_t)g->n * Fc, 256);                    // zb
     b += align_up(sizeof(int32_t) * (size_t)Fc, 256) * 3;     // active x2, norm_cnt
@@ -393,8 +426,9 @@ int decode_typed(const ldpc_graph* g, int64_t F, int max_iter, unsigned flags, c
     char* p = (char*)ws;
     auto take = [&](size_t bytes) { char* q = p; p += align_up(bytes, 256); return (void*)q; };
     T* lch = (T*)take(sizeof(T) * (size_t)g->n * Fc);
-    T* M = (T*)take(sizeof(T) * (size_t)g->nnz * Fc);
-    T* E = (T*)take(sizeof(T) * (size_t)g->nnz * Fc);
+    T* Ebuf[2];                                   // messages of the previous / the current pass
+    Ebuf[0] = (T*)take(sizeof(T) * (size_t)g->nnz * Fc);
+    Ebuf[1] = (T*)take(sizeof(T) * (size_t)g->nnz * Fc);
     T* post = (T*)take(sizeof(T) * (size_t)g->n * Fc);
     uint8_t* zb = (uint8_t*)take((size_t)g->n * Fc);
     ChunkState st;
@@ -434,13 +468,13 @@ int decode_typed(const ldpc_graph* g, int64_t F, int max_iter, unsigned flags, c
             const int last = it == max_iter - 1;
 #define LDPC_CN(MAXD)                                                                               \
     k_check_nodes<T, MAXD><<<cn_grid, kThreads, 0, stream>>>(g->m, g->d_row_ptr, g->d_col_idx, lch, \
-        M, E, Fci, st.active[par], cnt, st.done, first, fix_odd)
+        post, Ebuf[par ^ 1], Ebuf[par], Fci, st.active[par], cnt, st.done, first, fix_odd)
             if (g->max_cdeg <= 8) LDPC_CN(8);
             else if (g->max_cdeg <= 24) LDPC_CN(24);
             else LDPC_CN(0);
 #undef LDPC_CN
             LDPC_LAUNCH_CHECK();
-            k_var_nodes<T><<<vn_grid, kThreads, 0, stream>>>(g->n, g->d_col_ptr, g->d_csc_edge, lch, M, E, post,
+            k_var_nodes<T><<<vn_grid, kThreads, 0, stream>>>(g->n, g->d_col_ptr, g->d_csc_edge, lch, Ebuf[par], post,
                 zb, Fci, st.active[par], cnt, st.done, first, k_norm, st.norm_cnt);
             LDPC_LAUNCH_CHECK();
             // without early termination only the last pass needs a syndrome
