@@ -68,6 +68,9 @@ typedef enum ldpc_dtype {
 #define LDPC_FLAG_NO_JIT        0x20u /* resident path: never specialise the kernel at run time (NVRTC);
                                          unregistered base matrices then use the table-driven kernel */
 
+#define LDPC_FLAG_NORM_LLR      0x40u /* ldpc_mc_run: also accumulate the "normalized LLR" metric (spa_decoder.py:210-228)
+                                         in counters[5]; runs the generic kernels, which carry the metric */
+
 /* Which kernel family a (graph, dtype, flags) combination runs on (ldpc_graph_prepare). */
 typedef enum ldpc_kernel_kind {
     LDPC_KERNEL_GENERIC = 0,       /* frame-minor streaming kernels, any graph */
@@ -217,7 +220,10 @@ int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t frames, int m
  *   k_info             number of information bits; BER is taken over them (main.py:323-330)
  *   counters_dev       uint64[5], ACCUMULATED: frames, failed frames, info-bit errors counted in
  *                      failed frames only, sum of convergence iterations, converged frames
- *                      (main.py:314-339)
+ *                      (main.py:314-339).  With LDPC_FLAG_NORM_LLR the array is uint64[6]:
+ *                      counters[5] += sum over ALL frames of the exit pass' sign-change count over
+ *                      the first k_info bits with |L| <= 7 (spa_decoder.py:218-228); the reference's
+ *                      avg_normalized_llr of a point is counters[5] / (k_info * frames) (main.py:332-334,357)
  */
 int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
                 double speed, double snr_db, int sigma_sq_quirk,

@@ -298,7 +298,7 @@ extern "C" size_t ldpc_mc_workspace_bytes(const ldpc_graph* g, int64_t frames, i
     if (dtype == LDPC_F32_FAST && qc_resident_kind(g, 0) != LDPC_KERNEL_GENERIC) return 256;
     const size_t esz = dtype == LDPC_F64 ? 8 : 4;
     const int64_t F = std::max<int64_t>(frames, 1);
-    return align_up((size_t)F * g->n * esz, 256) + align_up((size_t)F * g->n, 256) + align_up((size_t)F * 4, 256) +
+    return align_up((size_t)F * g->n * esz, 256) + align_up((size_t)F * g->n, 256) + align_up((size_t)F * 4, 256) * 2 +
            align_up((size_t)F, 256) + generic_workspace_bytes(g, F, dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32);
 }
 
@@ -317,7 +317,8 @@ extern "C" int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int m
     if (codeword_stride != 0 && codeword_stride < g->n) { set_error("codeword_stride must be 0 or >= n"); return LDPC_ERR_INVALID; }
     if (frames == 0) return LDPC_OK;
     cudaStream_t stream = (cudaStream_t)stream_v;
-    if (use_resident(g, dtype, flags)) {
+    const bool want_norm = (flags & LDPC_FLAG_NORM_LLR) != 0;       // metric lives in the generic kernels
+    if (!want_norm && use_resident(g, dtype, flags)) {
         McParams mc;
         mc.active = true;
         channel_params(speed, snr_db, sigma_sq_quirk, seed, stream_id, &mc);
@@ -330,7 +331,7 @@ extern "C" int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int m
         return qc_resident_decode(g, frames, max_iter, flags, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                   mc, workspace_dev, workspace_bytes, stream);
     }
-    if (dtype == LDPC_F32_FAST && !(flags & LDPC_FLAG_FORCE_GENERIC)) {
+    if (dtype == LDPC_F32_FAST && !(flags & LDPC_FLAG_FORCE_GENERIC) && !want_norm) {
         set_error("LDPC_F32_FAST needs a quasi-cyclic graph supported by the resident kernel");
         return LDPC_ERR_UNSUPPORTED;
     }
@@ -339,7 +340,7 @@ extern "C" int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int m
     const size_t esz = gd == LDPC_F64 ? 8 : 4;
     const int n = g->n;
     auto need = [&](int64_t F) {
-        return align_up((size_t)F * n * esz, 256) + align_up((size_t)F * n, 256) + align_up((size_t)F * 4, 256) +
+        return align_up((size_t)F * n * esz, 256) + align_up((size_t)F * n, 256) + align_up((size_t)F * 4, 256) * 2 +
                align_up((size_t)F, 256) + generic_workspace_bytes(g, F, gd);
     };
     int64_t chunk = (frames + 31) / 32 * 32;
@@ -353,16 +354,18 @@ extern "C" int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int m
     uint8_t* z = (uint8_t*)p; p += align_up((size_t)chunk * n, 256);
     int32_t* conv = (int32_t*)p; p += align_up((size_t)chunk * 4, 256);
     uint8_t* ok = (uint8_t*)p; p += align_up((size_t)chunk, 256);
+    float* norm = (float*)p; p += align_up((size_t)chunk * 4, 256);
+    if (!want_norm) norm = nullptr;
     const size_t ws_bytes = workspace_bytes - (size_t)(p - (char*)workspace_dev);
     for (int64_t f0 = 0; f0 < frames; f0 += chunk) {
         const int64_t c = std::min<int64_t>(chunk, frames - f0);
         rc = channel_fill(n, gd, c, speed, snr_db, sigma_sq_quirk, seed, stream_id, frame_offset + (uint64_t)f0,
                           codeword_dev ? codeword_dev + f0 * codeword_stride : nullptr, codeword_stride, llr, stream);
         if (rc) return rc;
-        rc = generic_decode(g, gd, c, max_iter, flags, llr, z, conv, ok, nullptr, nullptr, 0, p, ws_bytes, stream);
+        rc = generic_decode(g, gd, c, max_iter, flags, llr, z, conv, ok, nullptr, norm, k_info, p, ws_bytes, stream);
         if (rc) return rc;
         rc = count_errors(n, k_info, c, z, ok, conv, codeword_dev ? codeword_dev + f0 * codeword_stride : nullptr, codeword_stride,
-                          info_mask_dev, (unsigned long long*)counters_dev, stream);
+                          info_mask_dev, norm, k_info, (unsigned long long*)counters_dev, stream);
         if (rc) return rc;
     }
     return LDPC_OK;

@@ -115,6 +115,7 @@ int channel_fill(int n, int dtype, int64_t frames, double speed, double snr_db, 
 void channel_params(double speed, double snr_db, int quirk, uint64_t seed, uint32_t stream_id, McParams* mc);
 int count_errors(int n, int k_info, int64_t frames, const uint8_t* z_dev, const uint8_t* ok_dev,
                  const int32_t* conv_dev, const uint8_t* codeword_dev, int64_t codeword_stride,
-                 const uint8_t* info_mask_dev, unsigned long long* counters_dev, cudaStream_t stream);
+                 const uint8_t* info_mask_dev, const float* norm_dev, int k_norm,
+                 unsigned long long* counters_dev, cudaStream_t stream);
 
 }  // namespace ldpc

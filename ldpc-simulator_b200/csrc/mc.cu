@@ -45,15 +45,16 @@ __global__ void __launch_bounds__(256)
 k_count_errors(int n, int k_info, int64_t frames, const uint8_t* __restrict__ z,
                const uint8_t* __restrict__ ok, const int32_t* __restrict__ conv,
                const uint8_t* __restrict__ codeword_base, long long cw_stride,
-               const uint8_t* __restrict__ info_mask, unsigned long long* __restrict__ counters)
+               const uint8_t* __restrict__ info_mask, const float* __restrict__ norm, int k_norm,
+               unsigned long long* __restrict__ counters)
 {
-    __shared__ unsigned long long acc[5];
-    if (threadIdx.x < 5) acc[threadIdx.x] = 0;
+    __shared__ unsigned long long acc[6];
+    if (threadIdx.x < 6) acc[threadIdx.x] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    unsigned long long c_fr = 0, c_fe = 0, c_be = 0, c_cs = 0, c_cc = 0;
+    unsigned long long c_fr = 0, c_fe = 0, c_be = 0, c_cs = 0, c_cc = 0, c_nl = 0;
     for (int64_t f = warp0; f < frames; f += nwarps) {
         const bool good = ok[f] != 0;
         if (!good) {                                                     // main.py:326
@@ -74,14 +75,17 @@ k_count_errors(int n, int k_info, int64_t frames, const uint8_t* __restrict__ z,
             c_fr += 1;
             const int ci = conv[f];
             if (ci >= 0) { c_cs += (unsigned)ci; c_cc += 1; }            // :336-339
+            // :218-228,332-334: sign changes of the exit pass over the first k_norm bits, every frame
+            if (norm) c_nl += (unsigned long long)__float2ll_rn(norm[f] * (float)k_norm);
         }
     }
     if (lane == 0) {
         atomicAdd(&acc[0], c_fr); atomicAdd(&acc[1], c_fe); atomicAdd(&acc[2], c_be);
         atomicAdd(&acc[3], c_cs); atomicAdd(&acc[4], c_cc);
+        if (norm) atomicAdd(&acc[5], c_nl);
     }
     __syncthreads();
-    if (threadIdx.x < 5 && acc[threadIdx.x]) atomicAdd(&counters[threadIdx.x], acc[threadIdx.x]);
+    if (threadIdx.x < (norm ? 6 : 5) && acc[threadIdx.x]) atomicAdd(&counters[threadIdx.x], acc[threadIdx.x]);
 }
 
 }  // namespace
@@ -129,14 +133,15 @@ void channel_params(double speed, double snr_db, int quirk, uint64_t seed, uint3
 
 int count_errors(int n, int k_info, int64_t frames, const uint8_t* z_dev, const uint8_t* ok_dev,
                  const int32_t* conv_dev, const uint8_t* codeword_dev, int64_t codeword_stride,
-                 const uint8_t* info_mask_dev, unsigned long long* counters_dev, cudaStream_t stream)
+                 const uint8_t* info_mask_dev, const float* norm_dev, int k_norm,
+                 unsigned long long* counters_dev, cudaStream_t stream)
 {
     if (frames == 0) return LDPC_OK;
     DeviceInfo di;
     int rc = get_device_info(&di);
     if (rc) return rc;
     const int grid = (int)std::min<int64_t>((frames * 32 + 255) / 256, (int64_t)di.sm_count * 8);
-    k_count_errors<<<grid, 256, 0, stream>>>(n, k_info, frames, z_dev, ok_dev, conv_dev, codeword_dev, codeword_stride, info_mask_dev, counters_dev);
+    k_count_errors<<<grid, 256, 0, stream>>>(n, k_info, frames, z_dev, ok_dev, conv_dev, codeword_dev, codeword_stride, info_mask_dev, norm_dev, k_norm, counters_dev);
     LDPC_LAUNCH_CHECK();
     return LDPC_OK;
 }

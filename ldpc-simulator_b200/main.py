@@ -10,7 +10,9 @@ frame is generated, decoded and counted on the GPU (mc_driver.MonteCarloEngine).
 ``torch.distributed`` is initialised, from sharding frames over ranks.
 
 Only the pipeline the north-star names is supported: mode 1 (AWGN), modulation 1 (BPSK),
-standard encoding, no interleaver; anything else raises ``NotImplementedError``.
+standard encoding; other modes / encoders raise ``NotImplementedError``.  Interleaver settings are
+recorded but are a statistical no-op on this memoryless channel.  ``--adaptive`` runs the sweep
+under ``adaptive.AdaptiveController`` (main.py:620-639 of the reference).
 """
 from __future__ import annotations
 
@@ -52,8 +54,9 @@ def _check_scope(settings, args, encoding_method):
         raise NotImplementedError("only channel mode 1 (AWGN) with modulation 1 (BPSK) is supported")
     if encoding_method != EncodingMethod.STANDARD:
         raise NotImplementedError("only the standard (generator matrix) encoder is supported")
-    if settings.get_interleaver_type() != InterleaverType.NONE:
-        raise NotImplementedError("interleavers are outside the decode path (memoryless channel)")
+    # An interleaver setting is accepted and reported but moves no data: the channel is memoryless and
+    # the reference de-interleaves with the same permutation before decoding (main.py:104-112), so no
+    # statistic can depend on it.
 
 
 def run_simulation(encoder_decoder_data, settings, args, encoding_method, ru_data=None):
@@ -71,10 +74,8 @@ def run_simulation(encoder_decoder_data, settings, args, encoding_method, ru_dat
         fix_odd_check_sign=getattr(settings, "is_fix_odd_check_sign", lambda: False)(),
         sigma_sq_quirk=not getattr(args, "no_sigma_sq_quirk", False),
         seed=getattr(args, "seed", None) if getattr(args, "seed", None) is not None else int(time.time() * 1e6) % (2 ** 63),
+        normalized_llr=bool(getattr(args, "normalized_llr", False)),
     )
-    if getattr(args, "normalized_llr", False):
-        say("note: the normalized-LLR metric is produced by SPA_Decoder.decode_batch, not by the Monte-Carlo kernel; "
-            "avg_normalized_llr is reported as 0")
     say("Processing blocks over the SNR grid...")
     say("-" * 60)
     k = encoder_decoder_data._k
@@ -86,6 +87,9 @@ def run_simulation(encoder_decoder_data, settings, args, encoding_method, ru_dat
                                interval_frames=getattr(args, "interval_frames", None))
         avg_fer = cnt.frame_errors / args.blocks if args.fer else 0.0
         avg_ber = (cnt.bit_errors / (k * args.blocks) if k * args.blocks > 0 else 0.0) if args.ber else 0.0
+        avg_norm = cnt.avg_normalized_llr(k) if getattr(args, "normalized_llr", False) else 0.0      # main.py:357
+        if getattr(args, "normalized_llr", False):
+            say(f"  Normalized LLR: {avg_norm:.6f}")
         if args.fer:
             say(f"  FER: {avg_fer:.6f}")
         if args.ber:
@@ -93,7 +97,7 @@ def run_simulation(encoder_decoder_data, settings, args, encoding_method, ru_dat
         ok_blocks = cnt.frames - cnt.frame_errors
         say(f"  Decoded successfully: {ok_blocks}/{args.blocks} ({100.0 * ok_blocks / args.blocks:.2f}%)")
         snr_points.append(SNRPointResult(
-            snr_db=current_snr, ber=avg_ber, fer=avg_fer, avg_normalized_llr=0.0,
+            snr_db=current_snr, ber=avg_ber, fer=avg_fer, avg_normalized_llr=avg_norm,
             total_blocks=args.blocks, successful_blocks=ok_blocks, failed_blocks=cnt.frame_errors,
             avg_convergence_iterations=cnt.avg_conv(), matrix_path=args.matrix,
             modulation=args.modulation, max_iterations=args.iterations, interleaver=args.interleaver,
@@ -129,6 +133,11 @@ def build_parser():
     p.add_argument("--normalized-llr", action="store_true")
     p.add_argument("--encoding-method", "-e", type=str, choices=["standard", "richardson-urbanke"], default="standard")
     p.add_argument("--threads", "-t", type=int, default=1)
+    p.add_argument("--adaptive", action="store_true")
+    p.add_argument("--adaptive-strategy", type=str, choices=["threshold"], default="threshold")
+    p.add_argument("--matrix-dir", type=str, default=None)
+    p.add_argument("--adaptive-high-ber", type=float, default=1e-2)
+    p.add_argument("--adaptive-low-ber", type=float, default=1e-5)
     p.add_argument("--output-json", type=str, default=None)
     p.add_argument("--output-csv", type=str, default=None)
     # B200 additions
@@ -161,7 +170,14 @@ def main(argv=None):
     st.set_early_termination(not args.no_early_termination)
     st.set_fix_odd_check_sign(args.fix_odd_check_sign)
     method = EncodingMethod.STANDARD if args.encoding_method == "standard" else EncodingMethod.RICHARDSON_URBANKE
-    result = run_simulation(edd, st, args, method)
+    if args.adaptive:                                                      # main.py:620-639
+        from adaptive import AdaptiveController, ThresholdStrategy
+        from matrix_catalog import MatrixCatalog
+        matrix_dir = args.matrix_dir or os.path.join(os.path.dirname(os.path.abspath(args.matrix)), "..")
+        strategy = ThresholdStrategy(high_ber_threshold=args.adaptive_high_ber, low_ber_threshold=args.adaptive_low_ber)
+        result = AdaptiveController(strategy, MatrixCatalog(matrix_dir)).run_adaptive_sweep(edd, st, args, method)
+    else:
+        result = run_simulation(edd, st, args, method)
     if args.output_json:
         result.to_json(args.output_json)
     if args.output_csv:

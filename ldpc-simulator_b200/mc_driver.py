@@ -33,6 +33,7 @@ class PointCounters:
     bit_errors: int = 0
     conv_sum: int = 0
     conv_count: int = 0
+    norm_sum: int = 0          # sign changes of the exit pass (normalized-LLR metric), all frames
 
     def fer(self):
         return self.frame_errors / self.frames if self.frames else 0.0
@@ -42,6 +43,10 @@ class PointCounters:
 
     def avg_conv(self):
         return self.conv_sum / self.conv_count if self.conv_count else 0.0
+
+    def avg_normalized_llr(self, k):
+        """main.py:332-334,357: mean over the frames of (sign changes over the first k bits) / k."""
+        return self.norm_sum / (k * self.frames) if self.frames and k else 0.0
 
 
 def wilson_interval(errors, trials, z=1.959963984540054):
@@ -65,7 +70,7 @@ def split_frames(total, rank, world):
 class MonteCarloEngine:
     def __init__(self, edd, *, graph="std", precision="f64", max_iterations=20, early_termination=True,
                  fix_odd_check_sign=False, sigma_sq_quirk=True, seed=0x5EED, device=None, group=None,
-                 kernel_flags=0):
+                 kernel_flags=0, normalized_llr=False):
         import torch
         self.torch = torch
         self.edd = edd
@@ -75,6 +80,9 @@ class MonteCarloEngine:
         self.max_iterations = int(max_iterations)
         self.flags = (_native.FLAG_EARLY_TERM if early_termination else 0) | \
                      (_native.FLAG_FIX_ODD_SIGN if fix_odd_check_sign else 0) | int(kernel_flags)
+        if normalized_llr:
+            # the metric (spa_decoder.py:210-228) is carried by the generic kernels only
+            self.flags |= _native.FLAG_NORM_LLR | _native.FLAG_FORCE_GENERIC
         self.quirk = int(bool(sigma_sq_quirk))
         self.seed = int(seed)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -95,7 +103,8 @@ class MonteCarloEngine:
 
     def _workspace(self, frames):
         torch = self.torch
-        need = int(_native.lib().ldpc_mc_workspace_bytes(self.graph.handle, frames, self.dtype))
+        ws_dtype = _native.LDPC_F32 if (self.flags & _native.FLAG_FORCE_GENERIC and self.dtype == _native.LDPC_F32_FAST) else self.dtype
+        need = int(_native.lib().ldpc_mc_workspace_bytes(self.graph.handle, frames, ws_dtype))
         free_b, _ = torch.cuda.mem_get_info(self.device)
         need = max(256, min(need, int(free_b * 0.7)))
         if self._ws is None or self._ws.numel() < need:
@@ -110,7 +119,8 @@ class MonteCarloEngine:
         return cw if self.graph_name == "std" else self.edd.to_alist_order(cw)
 
     def launch(self, frames_local, speed, snr_db, counters, *, codeword=None, frame_offset=0):
-        """Enqueue ``frames_local`` frames on the current stream, accumulating into ``counters`` (cuda int64[5]).
+        """Enqueue ``frames_local`` frames on the current stream, accumulating into ``counters`` (cuda int64[5],
+        or [6] with ``normalized_llr``).
         ``codeword``: cuda uint8 [n] (sent by every frame) or [frames_local, n] (one per frame) or None (all-zero)."""
         torch = self.torch
         if frames_local <= 0:
@@ -158,8 +168,8 @@ def run_intervals(launch, *, device, rank, world, group, distributed, frames=Non
                   max_frames=None, interval_frames=None, frame_cursor=0):
     """Host logic of one SNR point, independent of the device that runs ``launch``.
 
-    ``launch(frames_local, counters, frame_offset)`` must accumulate this rank's five counters into
-    ``counters`` (int64[5] on ``device``).  Per interval: shard frames over ranks, launch, ONE
+    ``launch(frames_local, counters, frame_offset)`` must accumulate this rank's counters into
+    ``counters`` (int64[6] on ``device``: the five of main.py:314-339 plus the normalized-LLR sum).  Per interval: shard frames over ranks, launch, ONE
     all-reduce of the counters, then evaluate the stopping rule on the reduced values (so every rank
     takes the same decision).  Returns (PointCounters, new frame cursor).
     """
@@ -174,14 +184,14 @@ def run_intervals(launch, *, device, rank, world, group, distributed, frames=Non
     while done < budget:
         chunk = min(interval, budget - done)
         lo, hi = split_frames(chunk, rank, world)
-        counters = torch.zeros(5, dtype=torch.int64, device=device)
+        counters = torch.zeros(6, dtype=torch.int64, device=device)
         # ranks number their frames from the shared cursor; their Philox streams differ by stream_id = rank
         launch(hi - lo, counters, frame_cursor + lo)
         if distributed:
             dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=group)      # the one exchange step
         c = counters.cpu().tolist()
         total.frames += c[0]; total.frame_errors += c[1]; total.bit_errors += c[2]
-        total.conv_sum += c[3]; total.conv_count += c[4]
+        total.conv_sum += c[3]; total.conv_count += c[4]; total.norm_sum += c[5]
         done += chunk
         frame_cursor += chunk
         if frames is None and min_frame_errors is not None and total.frame_errors >= min_frame_errors:

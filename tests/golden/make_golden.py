@@ -424,6 +424,52 @@ def build_catalog_listing():
     log(repr(cat))
 
 
+def build_adaptive_strategy():
+    """adaptive.py:61-124 (ThresholdStrategy.evaluate) and :384-412 (_apply_action against the real catalog)
+    on a grid of point results -> expected actions / state transitions."""
+    from adaptive import AdaptiveController, AdaptiveState, ThresholdStrategy
+    from matrix_catalog import MatrixCatalog
+    from results import SNRPointResult
+    cases = []
+    strategies = [dict(), dict(high_ber_threshold=5e-2, low_ber_threshold=1e-4, fer_threshold=0.3, convergence_ratio=0.5)]
+    for si, kw in enumerate(strategies):
+        st = ThresholdStrategy(**kw)
+        for ber in (0.0, 1e-7, 9.99e-6, 1e-5, 5e-5, 1e-3, 1e-2, 1.0001e-2, 0.05, 0.2):
+            for fer in (0.0, 0.3, 0.5, 0.5001, 1.0):
+                for conv, max_it in ((0.0, 5), (4.0, 5), (4.01, 5), (3.0, 50), (45.0, 50), (90.0, 100), (60.0, 64)):
+                    for il in ("none", "random"):
+                        state = AdaptiveState("x/wimax_576_0.5.alist.txt", 0.5, 1, max_it, il, "standard")
+                        pt = SNRPointResult(snr_db=1.0, ber=ber, fer=fer, avg_normalized_llr=0.0, total_blocks=100,
+                                            successful_blocks=50, failed_blocks=50, avg_convergence_iterations=conv)
+                        act = st.evaluate(state, pt)
+                        cases.append(dict(strategy=si, ber=ber, fer=fer, conv=conv, max_it=max_it, interleaver=il,
+                                          action=None if act is None else dict(
+                                              matrix=act.new_matrix_path, modulation=act.new_modulation,
+                                              max_iterations=act.new_max_iterations, interleaver=act.new_interleaver,
+                                              reason=act.reason)))
+    # rate ladder walks over the real catalog
+    cat = MatrixCatalog(DB)
+    ctl = AdaptiveController(ThresholdStrategy(), cat)
+    ctl._get_encoder_decoder_data = lambda path: None          # no matrix loading, only the state transition
+    walks = []
+    for start in ("Wimax LDPC Codes/wimax_576_0.5.alist.txt", "Wimax LDPC Codes/wimax_2304_0.83.alist.txt",
+                  "Standardized LDPC Codes/wigig_R063_N672_K420.alist.txt", "BCH_7_4_1_strip.alist.txt"):
+        for direction in ("__LOWER_RATE__", "__HIGHER_RATE__"):
+            path = os.path.join(DB, start)
+            info = ctl._find_current_matrix_info(path)
+            state = AdaptiveState(path, info.rate if info else 0.0, 1, 5, "none", "standard")
+            trail = []
+            for _ in range(6):
+                from adaptive import AdaptiveAction
+                with _quiet():
+                    ctl._apply_action(AdaptiveAction(new_matrix_path=direction), state, None, None, None)
+                trail.append([os.path.relpath(state.current_matrix_path, DB), state.current_rate])
+            walks.append(dict(start=start, direction=direction, trail=trail))
+    with open(os.path.join(HERE, "adaptive_strategy.json"), "w") as f:
+        json.dump(dict(strategies=strategies, cases=cases, walks=walks), f, separators=(",", ":"))
+    log(f"adaptive: {len(cases)} strategy cases, {len(walks)} catalog walks")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", nargs="*", default=None)
@@ -435,6 +481,7 @@ def main():
         "stdform": build_stdform,
         "bch_kat": build_bch_kat,
         "results": build_results_sample,
+        "adaptive": build_adaptive_strategy,
         "catalog": build_catalog_listing,
         # BCH(7,4) on H_std, reference channel conventions (sigma^2 quirk, speed 4/7), random codewords
         "bch_random": lambda: build_decode_set("bch74_std_random", "bch_7_4.std", 4096, [0, 1, 2, 3, 4, 5, 6],

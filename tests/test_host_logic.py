@@ -336,3 +336,54 @@ def test_snr_grid_and_frame_split():
             assert max(sizes) - min(sizes) <= 1
     lo, hi = wilson_interval(10243, 80000)
     assert lo == pytest.approx(0.12574, abs=2e-4) and hi == pytest.approx(0.13037, abs=2e-4)
+
+
+# ---- adaptive controller (policy + catalog walks; the sweep itself runs on the GPU) ------------
+def test_adaptive_strategy_equals_the_reference_on_a_grid_of_points():
+    """ThresholdStrategy.evaluate (adaptive.py:61-124): 1400 (BER, FER, convergence, budget, interleaver)
+    points x 2 threshold sets evaluated by the unmodified reference (make_golden.py: adaptive)."""
+    from adaptive import AdaptiveState, ThresholdStrategy
+    from results import SNRPointResult
+    with open(os.path.join(GOLDEN, "adaptive_strategy.json")) as f:
+        gold = json.load(f)
+    strategies = [ThresholdStrategy(**kw) for kw in gold["strategies"]]
+    assert strategies[0].get_name() == "threshold"
+    for c in gold["cases"]:
+        state = AdaptiveState("x/wimax_576_0.5.alist.txt", 0.5, 1, c["max_it"], c["interleaver"], "standard")
+        pt = SNRPointResult(snr_db=1.0, ber=c["ber"], fer=c["fer"], avg_normalized_llr=0.0, total_blocks=100,
+                            successful_blocks=50, failed_blocks=50, avg_convergence_iterations=c["conv"])
+        act = strategies[c["strategy"]].evaluate(state, pt)
+        want = c["action"]
+        if want is None:
+            assert act is None, c
+        else:
+            got = dict(matrix=act.new_matrix_path, modulation=act.new_modulation, max_iterations=act.new_max_iterations,
+                       interleaver=act.new_interleaver, reason=act.reason)
+            assert got == want, c
+
+
+def test_adaptive_rate_ladder_walks_equal_the_reference(tmp_path, capsys):
+    """AdaptiveController._apply_action (:384-412) against the catalog of the reference's database."""
+    from adaptive import AdaptiveAction, AdaptiveController, AdaptiveState, ThresholdStrategy
+    with open(os.path.join(GOLDEN, "catalog_listing.json")) as f:
+        listing = json.load(f)
+    for e in listing["entries"]:
+        p = tmp_path / e["rel"]
+        p.parent.mkdir(parents=True, exist_ok=True)
+        p.write_text(listing["first_lines"][e["rel"]] + "\n")
+    ctl = AdaptiveController(ThresholdStrategy(), MatrixCatalog(str(tmp_path)))
+    ctl._get_encoder_decoder_data = lambda path: None
+    with open(os.path.join(GOLDEN, "adaptive_strategy.json")) as f:
+        walks = json.load(f)["walks"]
+    assert len(walks) == 8
+    for w in walks:
+        path = str(tmp_path / w["start"])
+        info = ctl._find_current_matrix_info(path)
+        state = AdaptiveState(path, info.rate if info else 0.0, 1, 5, "none", "standard")
+        for rel, rate in w["trail"]:
+            ctl._apply_action(AdaptiveAction(new_matrix_path=w["direction"]), state, None, None, None)
+            assert (os.path.relpath(state.current_matrix_path, tmp_path), state.current_rate) == (rel, rate), w
+    # the other fields of an action are plain assignments (:404-412)
+    ctl._apply_action(AdaptiveAction(new_max_iterations=40, new_interleaver="random", new_modulation=2), state, None, None, None)
+    assert (state.current_max_iterations, state.current_interleaver, state.current_modulation) == (40, "random", 2)
+    capsys.readouterr()
