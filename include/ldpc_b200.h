@@ -71,6 +71,10 @@ typedef enum ldpc_dtype {
 #define LDPC_FLAG_NORM_LLR      0x40u /* ldpc_mc_run: also accumulate the "normalized LLR" metric (spa_decoder.py:210-228)
                                          in counters[5]; runs the generic kernels, which carry the metric */
 
+/* Channel flags (the sigma_sq_quirk argument of ldpc_mc_run / ldpc_channel_llr). */
+#define LDPC_CHANNEL_SIGMA_SQ   0x1
+#define LDPC_CHANNEL_AMP_07     0x2
+
 /* Which kernel family a (graph, dtype, flags) combination runs on (ldpc_graph_prepare). */
 typedef enum ldpc_kernel_kind {
     LDPC_KERNEL_GENERIC = 0,       /* frame-minor streaming kernels, any graph */
@@ -209,7 +213,9 @@ int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t frames, int m
  * (channel.py:38-81).
  *
  *   speed, snr_db      sigma = 1/sqrt(2*speed*10^(snr_db/10))       (channel.py:113)
- *   sigma_sq_quirk     1: noise stddev = sigma^2 as the reference does (channel.py:68); 0: sigma
+ *   sigma_sq_quirk     channel flags: LDPC_CHANNEL_SIGMA_SQ (1) = noise stddev sigma^2 as the reference
+ *                      does (channel.py:68), else sigma; LDPC_CHANNEL_AMP_07 (2) = symbols +-0.7
+ *                      ("modulation 2", channel.py:50-51) instead of +-1
  *   seed, stream_id, frame_offset
  *                      Philox key = seed; counter = (stream_id, frame_offset + frame, word) so that
  *                      ranks / launches draw disjoint streams

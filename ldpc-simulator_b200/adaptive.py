@@ -127,7 +127,7 @@ class AdaptiveController:
 
     def _engine(self, state, settings, args):
         from mc_driver import MonteCarloEngine
-        key = (state.current_matrix_path, state.current_max_iterations)
+        key = (state.current_matrix_path, state.current_max_iterations, state.current_modulation)
         if key not in self._engines:
             seed = getattr(args, "seed", None)
             self._engines[key] = MonteCarloEngine(
@@ -139,7 +139,8 @@ class AdaptiveController:
                 fix_odd_check_sign=getattr(settings, "is_fix_odd_check_sign", lambda: False)(),
                 sigma_sq_quirk=not getattr(args, "no_sigma_sq_quirk", False),
                 seed=seed if seed is not None else int(time.time() * 1e6) % (2 ** 63),
-                normalized_llr=bool(getattr(args, "normalized_llr", False)))
+                normalized_llr=bool(getattr(args, "normalized_llr", False)),
+                modulation=state.current_modulation)
         return self._engines[key]
 
     # ---- the sweep ---------------------------------------------------------------------------

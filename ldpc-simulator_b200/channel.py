@@ -1,16 +1,20 @@
-"""BPSK over AWGN -> channel LLRs (the decoder's input interface).
+"""Channel -> LLRs (the decoder's input interface).
 
 Mirrors ``Channel.create_channel`` / ``Channel.process`` of python_ldpc_app/channel.py
-(:102-125, :38-81) for mode 1 (AWGN) and modulation 1 (BPSK), including the two
-conventions the error-rate curves depend on:
+(:102-125, :38-81), including the conventions the error-rate curves depend on:
 
-* bit 0 -> symbol -1, bit 1 -> +1 (:49); LLR = 2 y / sigma^2 (:80), so LLR < 0 means bit 0;
-* the noise standard deviation is sigma**2, not sigma (:68) -- kept (``sigma_sq_quirk``).
+* bit 0 -> symbol -1, bit 1 -> +1 (:49) -- or -+0.7 for "modulation 2" (:50-51);
+  LLR = 2 y / sigma^2 (:80), so LLR < 0 means bit 0;
+* mode 1 (AWGN): the noise standard deviation is sigma**2, not sigma (:68) -- kept (``sigma_sq_quirk``);
+* modes 2 (partial-band interference, :83-96) and 3 (counter interference, :98-100) draw their noise from
+  the two Park-Miller / Box-Muller generators (``gen_ptr``, ``gen_ptr2``) exactly as the reference does
+  -- a deterministic stream, so ``process`` is bit-identical to the reference there (mode 2 also
+  consumes numpy's global RandomState for the hit decision, :86).  Host only: they are in no
+  benchmark configuration, the GPU generator covers mode 1.
 
 ``sigma = 1/sqrt(2 * speed * 10^(snr/10))`` (:113): ``speed`` plays the role of the code rate.
-Modes 2/3 (interference) and "QPSK" are outside the decode path.
 
-B200 additions: ``process_batch`` (host, vectorised, for the parity mode with host-fed
+B200 additions: ``process_batch`` (host, vectorised, mode 1, for the parity mode with host-fed
 LLRs) and ``device_llr`` (Philox generator on the GPU, csrc/awgn_philox.cuh).
 """
 from __future__ import annotations
@@ -37,9 +41,13 @@ class Channel:
     def seed(self, value):
         self._rng = np.random.RandomState(int(value) % (2 ** 31))
 
-    def _require_awgn_bpsk(self):
-        if self.mode != 1 or self.modulation != 1:
-            raise NotImplementedError("only mode 1 (AWGN) with modulation 1 (BPSK) is on the B200 decode path")
+    def _require_awgn(self):
+        if self.mode != 1:
+            raise NotImplementedError("only mode 1 (AWGN) is vectorised / on the GPU; modes 2 and 3 go through process()")
+
+    @property
+    def amplitude(self):
+        return 0.7 if self.modulation == 2 else 1.0         # :49-51 (any other value leaves the symbol at 0, as there)
 
     def _noise_dev(self):
         s = self.gen_ptr.sigma
@@ -47,18 +55,35 @@ class Channel:
 
     def process(self, data_buffer):
         """Append n LLRs to ``data_buffer._channel_data`` (a reused buffer grows, as in the reference)."""
-        self._require_awgn_bpsk()
         bits = np.asarray(data_buffer._encoded_data)
         if bits.size == 0:
             return
-        llr = self.process_batch(bits[None, :])[0]
-        data_buffer._channel_data.extend(float(v) for v in llr)
+        if self.mode == 1:
+            llr = self.process_batch(bits[None, :])[0]
+            data_buffer._channel_data.extend(float(v) for v in llr)
+            return
+        n = int(bits.size)
+        amp = self.amplitude if self.modulation in (1, 2) else 0.0
+        out = data_buffer._channel_data
+        for i in range(n):
+            bit = -amp if bits[i] == 0 else amp
+            if self.mode == 2:                                           # :83-96
+                hit = np.random.randint(0, n) / n < self.p               # numpy's global stream, as the reference
+                pom1 = self.gen_ptr.gauss(i)
+                if hit:
+                    out.append((bit + self.gen_ptr2.gauss(i) + pom1) * self.L_c2)
+                else:
+                    out.append((bit + pom1) * self.L_c1)
+            elif self.mode == 3:                                         # :98-100
+                pom1 = self.gen_ptr.gauss(i)
+                pom2 = self.gen_ptr2.gauss(i)
+                out.append(((bit + pom1 + pom2) * self.p + (bit + pom1) * (1 - self.p)) * self.L_c3)
 
     def process_batch(self, encoded):
-        """encoded [F, n] bits -> LLRs [F, n] float64 (host)."""
-        self._require_awgn_bpsk()
+        """encoded [F, n] bits -> LLRs [F, n] float64 (host, mode 1)."""
+        self._require_awgn()
         enc = np.asarray(encoded)
-        sym = np.where(enc == 0, -1.0, 1.0)
+        sym = np.where(enc == 0, -self.amplitude, self.amplitude)
         noise = self._rng.normal(0.0, self._noise_dev(), size=enc.shape)
         return 2.0 * (sym + noise) / (self.gen_ptr.sigma ** 2)
 
@@ -68,7 +93,7 @@ class Channel:
         import ctypes as C
         import torch
         import _native
-        self._require_awgn_bpsk()
+        self._require_awgn()
         if speed is None or snr_db is None:
             speed, snr_db = self._speed, self._snr_db
         tdt = torch.float64 if dtype == "f64" else torch.float32
@@ -83,7 +108,8 @@ class Channel:
                 stride = n
         _native.check(_native.lib().ldpc_channel_llr(
             n, _native.LDPC_F64 if dtype == "f64" else _native.LDPC_F32, frames, float(speed), float(snr_db),
-            int(self.sigma_sq_quirk), int(seed), int(stream_id), int(frame_offset),
+            int(bool(self.sigma_sq_quirk)) | (_native.CHANNEL_AMP_07 if self.modulation == 2 else 0),
+            int(seed), int(stream_id), int(frame_offset),
             cw.data_ptr() if cw is not None else None, stride, out.data_ptr(),
             torch.cuda.current_stream().cuda_stream))
         return out

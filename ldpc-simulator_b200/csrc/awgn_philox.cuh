@@ -54,6 +54,7 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& g0, fl
 struct ChannelConst {
     float noise_dev;   // sigma^2 (quirk) or sigma
     float llr_scale;   // 2 / sigma^2
+    float amp;         // symbol amplitude: 1 (modulation 1, :49) or 0.7 (modulation 2, :51)
     uint32_t k0, k1;   // Philox key = seed
     uint32_t stream_id;
 };
@@ -69,7 +70,7 @@ __device__ __forceinline__ void channel_llr4(const ChannelConst& cc, uint64_t fr
     box_muller(p.z, p.w, g[2], g[3]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float sym = ((bits4 >> i) & 1u) ? 1.0f : -1.0f;
+        const float sym = ((bits4 >> i) & 1u) ? cc.amp : -cc.amp;
         const float y = __fmaf_rn(cc.noise_dev, g[i], sym);
         out[i] = __fmul_rn(y, cc.llr_scale);
     }

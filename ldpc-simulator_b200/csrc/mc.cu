@@ -90,12 +90,15 @@ k_count_errors(int n, int k_info, int64_t frames, const uint8_t* __restrict__ z,
 
 }  // namespace
 
-static ChannelConst make_channel_const(double speed, double snr_db, int quirk, uint64_t seed, uint32_t stream_id)
+// channel_flags: LDPC_CHANNEL_SIGMA_SQ (the reference's noise deviation), LDPC_CHANNEL_AMP_07 (modulation 2)
+static ChannelConst make_channel_const(double speed, double snr_db, int channel_flags, uint64_t seed, uint32_t stream_id)
 {
+    const bool quirk = (channel_flags & LDPC_CHANNEL_SIGMA_SQ) != 0;
     const double sigma = 1.0 / std::sqrt(2.0 * speed * std::pow(10.0, snr_db * 0.1));   // channel.py:113
     ChannelConst cc;
     cc.noise_dev = (float)(quirk ? sigma * sigma : sigma);                              // channel.py:68
     cc.llr_scale = (float)(2.0 / (sigma * sigma));                                      // channel.py:80
+    cc.amp = (channel_flags & LDPC_CHANNEL_AMP_07) ? 0.7f : 1.0f;                       // channel.py:49,51
     cc.k0 = (uint32_t)seed;
     cc.k1 = (uint32_t)(seed >> 32);
     cc.stream_id = stream_id;
@@ -127,6 +130,7 @@ void channel_params(double speed, double snr_db, int quirk, uint64_t seed, uint3
     const ChannelConst cc = make_channel_const(speed, snr_db, quirk, seed, stream_id);
     mc->noise_dev = cc.noise_dev;
     mc->llr_scale = cc.llr_scale;
+    mc->amp = cc.amp;
     mc->seed = seed;
     mc->stream_id = stream_id;
 }

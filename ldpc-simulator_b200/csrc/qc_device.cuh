@@ -22,6 +22,7 @@ struct McParams {               // in-kernel channel (awgn_philox.cuh); enabled 
     bool active = false;
     float noise_dev = 1.f;      // sigma^2 (reference quirk, channel.py:68) or sigma
     float llr_scale = 2.f;      // 2 / sigma^2 (channel.py:80)
+    float amp = 1.f;            // symbol amplitude (channel.py:49,51)
     uint64_t seed = 0;
     uint32_t stream_id = 0;
     uint64_t frame_offset = 0;

@@ -99,7 +99,7 @@ k_qc_resident(const __grid_constant__ QcParams<MB, DC> p, const float* __restric
     if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
 
     ChannelConst cc;
-    cc.noise_dev = mc.noise_dev; cc.llr_scale = mc.llr_scale;
+    cc.noise_dev = mc.noise_dev; cc.llr_scale = mc.llr_scale; cc.amp = mc.amp;
     cc.k0 = (uint32_t)mc.seed; cc.k1 = (uint32_t)(mc.seed >> 32); cc.stream_id = mc.stream_id;
 
     for (long long f = blockIdx.x;; ) {

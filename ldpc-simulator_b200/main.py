@@ -9,8 +9,8 @@ frame is generated, decoded and counted on the GPU (mc_driver.MonteCarloEngine).
 ``args.threads`` is accepted and recorded; parallelism comes from the GPU batch and, when
 ``torch.distributed`` is initialised, from sharding frames over ranks.
 
-Only the pipeline the north-star names is supported: mode 1 (AWGN), modulation 1 (BPSK),
-standard encoding; other modes / encoders raise ``NotImplementedError``.  Interleaver settings are
+Only the pipeline the north-star names is supported: mode 1 (AWGN), modulation 1 (BPSK, or the
+reference's "modulation 2" = symbols of amplitude 0.7), standard encoding; other modes / encoders raise ``NotImplementedError``.  Interleaver settings are
 recorded but are a statistical no-op on this memoryless channel.  ``--adaptive`` runs the sweep
 under ``adaptive.AdaptiveController`` (main.py:620-639 of the reference).
 """
@@ -50,8 +50,9 @@ def snr_grid(initial_snr, end_snr, step_snr):
 
 
 def _check_scope(settings, args, encoding_method):
-    if getattr(args, "mode", 1) != 1 or getattr(args, "modulation", 1) != 1:
-        raise NotImplementedError("only channel mode 1 (AWGN) with modulation 1 (BPSK) is supported")
+    if getattr(args, "mode", 1) != 1:
+        raise NotImplementedError("the GPU channel generator covers mode 1 (AWGN); modes 2 and 3 exist on the host "
+                                  "(Channel.process) only")
     if encoding_method != EncodingMethod.STANDARD:
         raise NotImplementedError("only the standard (generator matrix) encoder is supported")
     # An interleaver setting is accepted and reported but moves no data: the channel is memoryless and
@@ -75,6 +76,7 @@ def run_simulation(encoder_decoder_data, settings, args, encoding_method, ru_dat
         sigma_sq_quirk=not getattr(args, "no_sigma_sq_quirk", False),
         seed=getattr(args, "seed", None) if getattr(args, "seed", None) is not None else int(time.time() * 1e6) % (2 ** 63),
         normalized_llr=bool(getattr(args, "normalized_llr", False)),
+        modulation=getattr(args, "modulation", 1),
     )
     say("Processing blocks over the SNR grid...")
     say("-" * 60)

@@ -70,7 +70,7 @@ def split_frames(total, rank, world):
 class MonteCarloEngine:
     def __init__(self, edd, *, graph="std", precision="f64", max_iterations=20, early_termination=True,
                  fix_odd_check_sign=False, sigma_sq_quirk=True, seed=0x5EED, device=None, group=None,
-                 kernel_flags=0, normalized_llr=False):
+                 kernel_flags=0, normalized_llr=False, modulation=1):
         import torch
         self.torch = torch
         self.edd = edd
@@ -83,7 +83,8 @@ class MonteCarloEngine:
         if normalized_llr:
             # the metric (spa_decoder.py:210-228) is carried by the generic kernels only
             self.flags |= _native.FLAG_NORM_LLR | _native.FLAG_FORCE_GENERIC
-        self.quirk = int(bool(sigma_sq_quirk))
+        # channel flags of ldpc_mc_run: the reference's noise deviation, +-0.7 symbols for modulation 2
+        self.quirk = int(bool(sigma_sq_quirk)) | (_native.CHANNEL_AMP_07 if int(modulation) == 2 else 0)
         self.seed = int(seed)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.group = group

@@ -286,19 +286,19 @@ double spa_oracle_sigma(double speed, double snr_db)
 }
 
 /*
- * channel.py:38-81, mode 1, modulation 1 (BPSK), with the noise samples given
+ * channel.py:38-81, mode 1, modulation 1 (BPSK) or 2 (amplitude 0.7), with the noise samples given
  * by the caller as unit normals g[]:  symbol = -1 for bit 0, +1 for bit 1
  * (:49); noise = g * sigma^2 when sigma_sq_quirk (the reference passes
  * sigma**2 as the *standard deviation*, :68) else g * sigma; y = symbol +
  * noise (:76); LLR = 2*y/sigma^2 (:80).
  */
 void spa_oracle_channel_llr(int64_t count, const uint8_t *bits, const double *g,
-                            double sigma, int sigma_sq_quirk, double *llr)
+                            double sigma, int sigma_sq_quirk, double amp, double *llr)
 {
     const double s2 = sigma * sigma;
     const double dev = sigma_sq_quirk ? s2 : sigma;
     for (int64_t q = 0; q < count; ++q) {
-        double sym = bits[q] == 0 ? -1.0 : 1.0;
+        double sym = bits[q] == 0 ? -amp : amp;     /* amp = 1 (modulation 1, :49) or 0.7 (modulation 2, :51) */
         double y = sym + dev * g[q];
         llr[q] = 2.0 * y / s2;
     }

@@ -44,7 +44,7 @@ def _load():
     lib.spa_oracle_sigma.restype = C.c_double
     lib.spa_oracle_sigma.argtypes = [C.c_double, C.c_double]
     lib.spa_oracle_channel_llr.restype = None
-    lib.spa_oracle_channel_llr.argtypes = [C.c_int64, u8p, f64p, C.c_double, C.c_int, f64p]
+    lib.spa_oracle_channel_llr.argtypes = [C.c_int64, u8p, f64p, C.c_double, C.c_int, C.c_double, f64p]
     lib.spa_oracle_count_errors.restype = None
     lib.spa_oracle_count_errors.argtypes = [C.c_int64, C.c_int, C.c_int, u8p, u8p, i32p, u8p, u64p]
     lib.spa_oracle_standard_form.restype = C.c_int
@@ -117,13 +117,13 @@ def sigma(speed, snr_db):
     return float(_load().spa_oracle_sigma(float(speed), float(snr_db)))
 
 
-def channel_llr(bits, unit_normals, sig, sigma_sq_quirk=True):
-    """channel.py:49,68,76,80 with caller-supplied unit normals."""
+def channel_llr(bits, unit_normals, sig, sigma_sq_quirk=True, amp=1.0):
+    """channel.py:49-51,68,76,80 with caller-supplied unit normals."""
     bits = np.ascontiguousarray(bits, dtype=np.uint8)
     g = np.ascontiguousarray(unit_normals, dtype=np.float64)
     out = np.empty(g.shape, dtype=np.float64)
     _load().spa_oracle_channel_llr(g.size, _p(bits, C.c_uint8), _p(g, C.c_double), float(sig),
-                                   int(bool(sigma_sq_quirk)), _p(out, C.c_double))
+                                   int(bool(sigma_sq_quirk)), float(amp), _p(out, C.c_double))
     return out
 
 

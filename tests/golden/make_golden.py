@@ -470,6 +470,35 @@ def build_adaptive_strategy():
     log(f"adaptive: {len(cases)} strategy cases, {len(walks)} catalog walks")
 
 
+def build_channel_modes():
+    """channel.py:38-100 for modes 2 and 3 (and modulation 2): the noise comes from the Park-Miller generators
+    seeded with IDUM1 / IDUM2 (deterministic), the hit decision of mode 2 from numpy's global RandomState."""
+    from channel import Channel
+
+    class Buf:
+        def __init__(self, bits):
+            self._encoded_data = list(bits)
+            self._channel_data = []
+
+    rng = np.random.default_rng(99)
+    cases = []
+    for mode, mod, p, speed, sn1, sn2 in ((2, 1, 0.3, 0.5, 3.0, 1.0), (2, 2, 0.7, 0.5, 1.0, -2.0), (3, 1, 0.25, 0.75, 2.0, 0.0),
+                                          (3, 2, 0.9, 0.5, 4.0, 4.0), (2, 1, 1.0, 1.0, 0.0, 0.0)):
+        bits = [int(b) for b in rng.integers(0, 2, size=96)]
+        ch = Channel.create_channel(speed, sn1, sn2, mode, p, mod)
+        np.random.seed(4242)
+        out = []
+        for _frame in range(2):                 # the generators keep their state from frame to frame
+            buf = Buf(bits)
+            ch.process(buf)
+            out.append(buf._channel_data)
+        cases.append(dict(mode=mode, modulation=mod, p=p, speed=speed, sn1=sn1, sn2=sn2, bits=bits, numpy_seed=4242,
+                          L_c=[ch.L_c1, ch.L_c2, ch.L_c3], sigma=[ch.gen_ptr.sigma, ch.gen_ptr2.sigma], llr=out))
+    with open(os.path.join(HERE, "channel_modes.json"), "w") as f:
+        json.dump(dict(cases=cases), f)
+    log(f"channel modes: {len(cases)} cases")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", nargs="*", default=None)
@@ -482,6 +511,7 @@ def main():
         "bch_kat": build_bch_kat,
         "results": build_results_sample,
         "adaptive": build_adaptive_strategy,
+        "channel_modes": build_channel_modes,
         "catalog": build_catalog_listing,
         # BCH(7,4) on H_std, reference channel conventions (sigma^2 quirk, speed 4/7), random codewords
         "bch_random": lambda: build_decode_set("bch74_std_random", "bch_7_4.std", 4096, [0, 1, 2, 3, 4, 5, 6],

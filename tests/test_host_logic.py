@@ -307,8 +307,8 @@ def test_channel_matches_oracle_formula():
     buf._encoded_data = [0, 1, 1, 0]
     ch.process(buf); ch.process(buf)
     assert len(buf._channel_data) == 8                         # appends (channel.py:81)
-    with pytest.raises(NotImplementedError):
-        Channel.create_channel(0.5, 2.0, 1.0, 2, 0.1, 1).process(buf)
+    with pytest.raises(NotImplementedError):                   # modes 2/3 exist per frame on the host only
+        Channel.create_channel(0.5, 2.0, 1.0, 2, 0.1, 1).process_batch(bits)
 
 
 def test_lcg_generator_is_park_miller():
@@ -387,3 +387,39 @@ def test_adaptive_rate_ladder_walks_equal_the_reference(tmp_path, capsys):
     ctl._apply_action(AdaptiveAction(new_max_iterations=40, new_interleaver="random", new_modulation=2), state, None, None, None)
     assert (state.current_max_iterations, state.current_interleaver, state.current_modulation) == (40, "random", 2)
     capsys.readouterr()
+
+
+def test_channel_modes_2_and_3_are_bit_identical_to_the_reference():
+    """channel.py:83-100: interference modes on the Park-Miller generators (+ numpy's global stream for the
+    hit decision of mode 2), both modulations; two consecutive frames so the generator state carries over."""
+    from channel import Channel
+    with open(os.path.join(GOLDEN, "channel_modes.json")) as f:
+        cases = json.load(f)["cases"]
+    assert {c["mode"] for c in cases} == {2, 3}
+
+    class Buf:
+        def __init__(self, bits):
+            self._encoded_data, self._channel_data = list(bits), []
+
+    for c in cases:
+        ch = Channel.create_channel(c["speed"], c["sn1"], c["sn2"], c["mode"], c["p"], c["modulation"])
+        assert [ch.L_c1, ch.L_c2, ch.L_c3] == c["L_c"] and [ch.gen_ptr.sigma, ch.gen_ptr2.sigma] == c["sigma"]
+        np.random.seed(c["numpy_seed"])
+        for want in c["llr"]:
+            buf = Buf(c["bits"])
+            ch.process(buf)
+            assert buf._channel_data == want, (c["mode"], c["modulation"])
+
+
+def test_modulation_2_uses_symbols_of_amplitude_07():
+    from channel import Channel
+    a = Channel.create_channel(0.5, 2.0, 0.0, 1, 0.1, 1); a.seed(3)
+    b = Channel.create_channel(0.5, 2.0, 0.0, 1, 0.1, 2); b.seed(3)
+    bits = np.array([[0, 1, 1, 0, 1]])
+    la, lb = a.process_batch(bits), b.process_batch(bits)
+    s2 = a.gen_ptr.sigma ** 2
+    np.testing.assert_allclose((la - lb) * s2 / 2.0, np.where(bits == 0, -0.3, 0.3), atol=1e-12)
+    from oracle import spa_oracle as oracle
+    want = oracle.channel_llr(bits.ravel(), (lb.ravel() * s2 / 2.0 - np.where(bits.ravel() == 0, -0.7, 0.7)) / s2,
+                              a.gen_ptr.sigma, True, amp=0.7)
+    np.testing.assert_allclose(lb.ravel(), want, rtol=1e-12)
