@@ -8,6 +8,9 @@ import sys
 import numpy as np
 import pytest
 
+# run-time specialised kernels (csrc/qc_jit.cu) cache their cubins here instead of ~/.cache during tests
+os.environ.setdefault("LDPC_JIT_CACHE", os.path.join(__import__("tempfile").gettempdir(), "ldpc_b200_jit_tests"))
+
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(REPO, "ldpc-simulator_b200")
 GOLDEN = os.path.join(REPO, "tests", "golden")
