@@ -247,6 +247,57 @@ k_check_nodes(int m, const int32_t* __restrict__ row_ptr, const int32_t* __restr
     }
 }
 
+// Check-node pass for SMALL batches (the per-frame SPA_Decoder.decode call): one warp = (check i,
+// frame slot t) with the LANES spread over the edges of the row, instead of one thread walking the
+// whole row for one of 32 frames.  tanh / division / atanh run lane-parallel; the product is still
+// taken sequentially in edge order (by one lane, from the tanh values parked in shared memory), so the
+// result is bit-identical to k_check_nodes.  Dynamic shared memory: warps per CTA x max degree values.
+constexpr int kSmallWarps = 4;
+template <typename T>
+__global__ void __launch_bounds__(kSmallWarps * 32)
+k_check_rows_small(int m, const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                   const T* __restrict__ lch, const T* __restrict__ post, const T* __restrict__ Eold,
+                   T* __restrict__ E, int Fc, const int32_t* __restrict__ active,
+                   const int32_t* __restrict__ count_ptr, const uint8_t* __restrict__ done,
+                   int first_pass, int fix_odd, int max_deg)
+{
+    extern __shared__ __align__(16) unsigned char small_smem[];
+    const int count = *count_ptr;
+    if (count <= 0) return;
+    const int lane = threadIdx.x & 31;
+    T* tv = reinterpret_cast<T*>(small_smem) + (size_t)(threadIdx.x >> 5) * max_deg;
+    const int64_t pairs = (int64_t)m * count;
+    const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < pairs; w += stride) {
+        const int t = (int)(w / m);
+        const int i = (int)(w - (int64_t)t * m);
+        const int f = active[t];
+        if (done[f]) continue;                                   // warp-uniform
+        const int a = row_ptr[i], d = row_ptr[i + 1] - a;
+        if (d == 0) continue;
+        for (int q = lane; q < d; q += 32)
+            tv[q] = tanh_half_clipped<T>(v2c_message<T>(lch, post, Eold, col_idx[a + q], a + q, Fc, f, first_pass));
+        __syncwarp();
+        T total = T(1);
+        for (int q = 0; q < d; ++q) total *= tv[q];             // every lane: same order, same value
+        for (int q = lane; q < d; q += 32) {
+            const T tq = tv[q];
+            T r;
+            if (Num<T>::abs_(tq) > Num<T>::small_tanh()) {
+                r = total / tq;
+            } else {
+                r = T(1);
+                for (int u = 0; u < d; ++u)
+                    if (u != q) r *= tv[u];
+            }
+            T e = T(2) * Num<T>::atanh_(clip_unit<T>(r));
+            if (fix_odd && (d & 1)) e = -e;
+            E[(size_t)(a + q) * Fc + f] = e;
+        }
+        __syncwarp();                                            // tv is reused by the next pair
+    }
+}
+
 // Posterior + hard decision (+ optional "normalized LLR" sign-change count over the
 // first k_info bits, spa_decoder.py:210-228).  The variable->check messages of
 // :260-268 are formed by the next check-node pass (v2c_message).
@@ -279,6 +330,72 @@ k_var_nodes(int n, const int32_t* __restrict__ col_ptr, const int32_t* __restric
         }
         post[(size_t)j * Fc + f] = L;
         zb[(size_t)j * Fc + f] = (uint8_t)(L < T(0));             // :188
+    }
+}
+
+// Small-batch twins of k_var_nodes / k_syndrome: one warp = (node, frame slot), lanes over the edges.
+// The posterior sum keeps the ascending check order of :177-182 (values parked in shared memory, one
+// lane adds them up), so it is bit-identical to k_var_nodes; the syndrome parity is order free.
+template <typename T>
+__global__ void __launch_bounds__(kSmallWarps * 32)
+k_var_cols_small(int n, const int32_t* __restrict__ col_ptr, const int32_t* __restrict__ csc_edge,
+                 const T* __restrict__ lch, const T* __restrict__ E, T* __restrict__ post,
+                 uint8_t* __restrict__ zb, int Fc, const int32_t* __restrict__ active,
+                 const int32_t* __restrict__ count_ptr, const uint8_t* __restrict__ done, int first_pass,
+                 int k_norm, int32_t* __restrict__ norm_cnt, int max_deg)
+{
+    extern __shared__ __align__(16) unsigned char small_smem[];
+    const int count = *count_ptr;
+    if (count <= 0) return;
+    const int lane = threadIdx.x & 31;
+    T* ev = reinterpret_cast<T*>(small_smem) + (size_t)(threadIdx.x >> 5) * max_deg;
+    const int64_t pairs = (int64_t)n * count;
+    const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < pairs; w += stride) {
+        const int t = (int)(w / n);
+        const int j = (int)(w - (int64_t)t * n);
+        const int f = active[t];
+        if (done[f]) continue;
+        const int a = col_ptr[j], d = col_ptr[j + 1] - a;
+        for (int q = lane; q < d; q += 32) ev[q] = E[(size_t)csc_edge[a + q] * Fc + f];
+        __syncwarp();
+        if (lane == 0) {
+            T s = T(0);
+            for (int q = 0; q < d; ++q) s += ev[q];
+            const T ch = lch[(size_t)j * Fc + f];
+            const T L = ch + s;
+            if (k_norm > 0 && j < k_norm) {
+                const T prior = first_pass ? ch : post[(size_t)j * Fc + f];
+                if (!(Num<T>::abs_(L) > T(7)) && prior * L < T(0)) atomicAdd(&norm_cnt[f], 1);
+            }
+            post[(size_t)j * Fc + f] = L;
+            zb[(size_t)j * Fc + f] = (uint8_t)(L < T(0));
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kSmallWarps * 32)
+k_syndrome_small(int m, const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                 const uint8_t* __restrict__ zb, int Fc, const int32_t* __restrict__ active,
+                 const int32_t* __restrict__ count_ptr, const uint8_t* __restrict__ done,
+                 uint8_t* __restrict__ failed)
+{
+    const int count = *count_ptr;
+    if (count <= 0) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t pairs = (int64_t)m * count;
+    const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < pairs; w += stride) {
+        const int t = (int)(w / m);
+        const int i = (int)(w - (int64_t)t * m);
+        const int f = active[t];
+        if (done[f]) continue;
+        unsigned par = 0;
+        for (int e = row_ptr[i] + lane; e < row_ptr[i + 1]; e += 32)
+            par ^= (unsigned)(zb[(size_t)col_idx[e] * Fc + f] ^ 1u);
+        const unsigned odd = __ballot_sync(0xffffffffu, par & 1u);
+        if (lane == 0 && (__popc(odd) & 1)) failed[f] = 1;
     }
 }
 
@@ -458,6 +575,19 @@ int decode_typed(const ldpc_graph* g, int64_t F, int max_iter, unsigned flags, c
         }
         k_init_chunk<<<std::min((Fci + 255) / 256, grid_cap), 256, 0, stream>>>(st, Fci, valid);
         LDPC_LAUNCH_CHECK();
+        // Few frames (the per-frame decode call): lanes across the row instead of across frames, when a row
+        // has more edges than the chunk has frames to fill a warp with.
+        const size_t small_smem_bytes = sizeof(T) * (size_t)kSmallWarps * g->max_cdeg;
+        const int64_t avg_cdeg = g->nnz / std::max(1, g->m);
+        const size_t small_vsmem_bytes = sizeof(T) * (size_t)kSmallWarps * std::max(1, g->max_vdeg);
+        const bool small_rows = valid <= 32 && valid * 4 <= std::max<int64_t>(4, avg_cdeg) &&
+                                small_smem_bytes <= (size_t)di.max_smem_optin && small_vsmem_bytes <= (size_t)di.max_smem_optin;
+        const int small_vgrid = (int)std::min<int64_t>(((int64_t)g->n * valid + kSmallWarps - 1) / kSmallWarps, (int64_t)grid_cap * 4);
+        if (small_rows && small_vsmem_bytes > 48 * 1024)
+            LDPC_CUDA_TRY(cudaFuncSetAttribute(k_var_cols_small<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_vsmem_bytes));
+        const int small_grid = (int)std::min<int64_t>(((int64_t)g->m * valid + kSmallWarps - 1) / kSmallWarps, (int64_t)grid_cap * 4);
+        if (small_rows && small_smem_bytes > 48 * 1024)
+            LDPC_CUDA_TRY(cudaFuncSetAttribute(k_check_rows_small<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes));
         const int64_t cn_items = (int64_t)g->m * Fc, vn_items = (int64_t)g->n * Fc;
         const int cn_grid = (int)std::min<int64_t>((cn_items + kThreads - 1) / kThreads, grid_cap);
         const int vn_grid = (int)std::min<int64_t>((vn_items + kThreads - 1) / kThreads, grid_cap);
@@ -469,18 +599,32 @@ int decode_typed(const ldpc_graph* g, int64_t F, int max_iter, unsigned flags, c
 #define LDPC_CN(MAXD)                                                                               \
     k_check_nodes<T, MAXD><<<cn_grid, kThreads, 0, stream>>>(g->m, g->d_row_ptr, g->d_col_idx, lch, \
         post, Ebuf[par ^ 1], Ebuf[par], Fci, st.active[par], cnt, st.done, first, fix_odd)
-            if (g->max_cdeg <= 8) LDPC_CN(8);
+            if (small_rows) {
+                k_check_rows_small<T><<<small_grid, kSmallWarps * 32, small_smem_bytes, stream>>>(
+                    g->m, g->d_row_ptr, g->d_col_idx, lch, post, Ebuf[par ^ 1], Ebuf[par], Fci, st.active[par], cnt,
+                    st.done, first, fix_odd, g->max_cdeg);
+            }
+            else if (g->max_cdeg <= 8) LDPC_CN(8);
             else if (g->max_cdeg <= 24) LDPC_CN(24);
             else LDPC_CN(0);
 #undef LDPC_CN
             LDPC_LAUNCH_CHECK();
-            k_var_nodes<T><<<vn_grid, kThreads, 0, stream>>>(g->n, g->d_col_ptr, g->d_csc_edge, lch, Ebuf[par], post,
-                zb, Fci, st.active[par], cnt, st.done, first, k_norm, st.norm_cnt);
+            if (small_rows)
+                k_var_cols_small<T><<<small_vgrid, kSmallWarps * 32, small_vsmem_bytes, stream>>>(
+                    g->n, g->d_col_ptr, g->d_csc_edge, lch, Ebuf[par], post, zb, Fci, st.active[par], cnt, st.done, first,
+                    k_norm, st.norm_cnt, g->max_vdeg);
+            else
+                k_var_nodes<T><<<vn_grid, kThreads, 0, stream>>>(g->n, g->d_col_ptr, g->d_csc_edge, lch, Ebuf[par], post,
+                    zb, Fci, st.active[par], cnt, st.done, first, k_norm, st.norm_cnt);
             LDPC_LAUNCH_CHECK();
             // without early termination only the last pass needs a syndrome
             if (early || last) {
-                k_syndrome<<<cn_grid, kThreads, 0, stream>>>(g->m, g->d_row_ptr, g->d_col_idx, zb, Fci,
-                    st.active[par], cnt, st.done, st.failed);
+                if (small_rows)
+                    k_syndrome_small<<<small_grid, kSmallWarps * 32, 0, stream>>>(g->m, g->d_row_ptr, g->d_col_idx, zb, Fci,
+                        st.active[par], cnt, st.done, st.failed);
+                else
+                    k_syndrome<<<cn_grid, kThreads, 0, stream>>>(g->m, g->d_row_ptr, g->d_col_idx, zb, Fci,
+                        st.active[par], cnt, st.done, st.failed);
                 LDPC_LAUNCH_CHECK();
             }
             k_finish_pass<<<std::min((Fci + kThreads - 1) / kThreads, grid_cap), kThreads, 0, stream>>>(

@@ -317,6 +317,30 @@ def test_run_time_specialised_kernel(name, table):
                 dec.decode_batch(llr, jit=False)
 
 
+@pytest.mark.parametrize("name,frames", [("bch_7_4.std", 1), ("wimax_576_0.5", 1), ("wimax_576_0.5.std", 1), ("wimax_576_0.5.std", 7),
+                                         ("wimax_576_0.5.std", 32), ("tanner_155_64.std", 3)])
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_small_batch_check_node_kernel_is_bit_identical(name, frames, precision):
+    """Few frames (SPA_Decoder.decode: one) run a check-node kernel with the lanes spread over the edges of a
+    row (csrc/spa_generic.cu: k_check_rows_small); the product keeps the reference's edge order, so every
+    output bit equals what the same frames give inside a large batch (thread = check x frame kernels)."""
+    code = load_code(name)
+    rng = np.random.default_rng(41)
+    llr = awgn_llr(rng, 96, code.n, np.resize(np.array([1.0, 3.0, 5.0]), 96))
+    llr[5] = 0.0                                        # all ties: the |t| <= 1e-10 branch (:162-164)
+    if precision == "f32":
+        llr = llr.astype(np.float32)
+    dec = make_decoder(code, 15, precision)
+    big = dec.decode_batch(llr, want_posterior=True, normalized_llr=True)
+    for lo in (0, 5, 40):
+        small = dec.decode_batch(llr[lo:lo + frames], want_posterior=True, normalized_llr=True)
+        for key in ("z", "ok", "conv_it", "post", "norm"):
+            assert np.array_equal(getattr(small, key), getattr(big, key)[lo:lo + frames]), (key, lo)
+    fixed = dec.decode_batch(llr[:frames], want_posterior=True, early_termination=False)
+    fixed_big = dec.decode_batch(llr, want_posterior=True, early_termination=False)
+    assert np.array_equal(fixed.post, fixed_big.post[:frames]) and np.array_equal(fixed.z, fixed_big.z[:frames])
+
+
 def test_early_termination_on_large_codes():
     """Config 3.  Frames leave the active set as soon as their syndrome vanishes (dynamic frame queue in
     the resident kernel, active-list compaction in the generic kernels); per-frame results must equal the
