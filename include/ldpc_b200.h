@@ -68,6 +68,8 @@ typedef enum ldpc_dtype {
 #define LDPC_FLAG_NO_JIT        0x20u /* resident path: never specialise the kernel at run time (NVRTC);
                                          unregistered base matrices then use the table-driven kernel */
 
+#define LDPC_FLAG_NO_REPLAY     0x80u /* ldpc_decode_batch_host: do not replay tiny calls (<= 32 frames, generic kernels)
+                                         from a captured CUDA graph; launch the kernels one by one (tests) */
 #define LDPC_FLAG_NORM_LLR      0x40u /* ldpc_mc_run: also accumulate the "normalized LLR" metric (spa_decoder.py:210-228)
                                          in counters[5]; runs the generic kernels, which carry the metric */
 

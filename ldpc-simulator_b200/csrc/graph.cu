@@ -236,7 +236,9 @@ extern "C" int ldpc_graph_create_csr(int m, int n, int64_t nnz, const int32_t* r
     DeviceInfo di;
     rc = get_device_info(&di);
     if (rc) return rc;
+    static std::atomic<uint64_t> next_serial{1};
     ldpc_graph* g = new (std::nothrow) ldpc_graph();
+    if (g) g->serial = next_serial.fetch_add(1);
     if (!g) { set_error("out of host memory"); return LDPC_ERR_NOMEM; }
     g->m = m; g->n = n; g->nnz = nnz; g->device = di.device;
     g->row_ptr.assign(row_ptr, row_ptr + m + 1);

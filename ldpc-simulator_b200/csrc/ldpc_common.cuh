@@ -75,6 +75,7 @@ struct ldpc_graph {
     // resident-kernel tables (built lazily by spa_qc_resident.cu)
     void* d_qc_tables = nullptr;
     int device = -1;
+    uint64_t serial = 0;            // unique per handle (keys of caches that must not alias a freed pointer)
 };
 
 namespace ldpc {

@@ -107,7 +107,7 @@ class SPA_Decoder:
             raise ValueError(f"unknown precision {name!r}")
         return name, _PRECISIONS[name]
 
-    def _flags(self, early_termination=None, compact=False, table_kernel=False, jit=True):
+    def _flags(self, early_termination=None, compact=False, table_kernel=False, jit=True, replay=True):
         s = self.m_pSettings
         early = getattr(s, "is_early_termination", lambda: True)() if early_termination is None else early_termination
         flags = _native.FLAG_EARLY_TERM if early else 0
@@ -117,6 +117,8 @@ class SPA_Decoder:
             flags |= _native.FLAG_TABLE_KERNEL
         if not jit:
             flags |= _native.FLAG_NO_JIT
+        if not replay:
+            flags |= _native.FLAG_NO_REPLAY
         if getattr(s, "is_fix_odd_check_sign", lambda: False)():
             flags |= _native.FLAG_FIX_ODD_SIGN
         return flags
@@ -124,11 +126,13 @@ class SPA_Decoder:
     # ---- batched decode, host buffers (the end-to-end call) -------------------------
     def decode_batch(self, llr, *, precision=None, early_termination=None, compact=False, want_z=True,
                      want_bits=False, want_posterior=False, normalized_llr=None, max_iterations=None,
-                     table_kernel=False, jit=True):
+                     table_kernel=False, jit=True, replay=True):
         """Decode F frames given as a host array ``llr`` [F, n] (numpy, or a pinned CPU torch tensor).
 
         ``table_kernel`` / ``jit=False`` pick the table-driven resident kernel instead of the one
         specialised for the base matrix (at build time, or with NVRTC at run time); for tests.
+        Calls of <= 32 frames on the generic kernels are replayed from a CUDA graph captured on the first
+        call with the same configuration (``replay=False`` launches the kernels one by one).
 
         Returns a ``BatchResult`` of host numpy arrays.  Host<->device copies are pipelined inside
         ``ldpc_decode_batch_host`` (pinned staging, several streams).
@@ -168,7 +172,7 @@ class SPA_Decoder:
         k_info = int(self.m_pData._n - self.m_pData._m) if calc_norm else 0
         ptr = lambda a: a.ctypes.data if a is not None else None
         _native.check(_native.lib().ldpc_decode_batch_host(
-            g.handle, dtype, frames, int(max_it), self._flags(early_termination, compact, table_kernel, jit), in_ptr,
+            g.handle, dtype, frames, int(max_it), self._flags(early_termination, compact, table_kernel, jit, replay), in_ptr,
             ptr(z), ptr(zbits), ptr(conv), ptr(ok), ptr(post), ptr(norm), k_info))
         del keep
         return BatchResult(z, zbits, ok, conv, post, norm)

@@ -341,6 +341,37 @@ def test_small_batch_check_node_kernel_is_bit_identical(name, frames, precision)
     assert np.array_equal(fixed.post, fixed_big.post[:frames]) and np.array_equal(fixed.z, fixed_big.z[:frames])
 
 
+@pytest.mark.parametrize("name,precision", [("bch_7_4.std", "f64"), ("wimax_576_0.5.std", "f64"), ("wimax_576_0.5", "f32"),
+                                            ("ccsds_128_64", "f64")])
+def test_tiny_host_calls_replayed_from_a_cuda_graph_give_the_same_results(name, precision):
+    """ldpc_decode_batch_host with <= 32 frames on the generic kernels captures H2D + every kernel of every
+    pass + D2H into a CUDA graph once and replays it (the per-frame SPA_Decoder.decode call is launch
+    bound): same outputs as launching one by one, for new inputs, other frame counts and output sets, and
+    the launch counter keeps counting the kernels a replay runs."""
+    import _native
+    code = load_code(name)
+    rng = np.random.default_rng(8)
+    dt = np.float64 if precision == "f64" else np.float32
+    llr = awgn_llr(rng, 64, code.n, np.resize(np.array([1.0, 4.0]), 64)).astype(dt)
+    dec = make_decoder(code, 12, precision)
+    per_call = None
+    for frames in (1, 1, 5, 32, 1):
+        for start in (0, 9, 31):
+            x = llr[start:start + frames]
+            plain = dec.decode_batch(x, want_posterior=True, normalized_llr=True, replay=False)
+            before = _native.launches()
+            fast = dec.decode_batch(x, want_posterior=True, normalized_llr=True)
+            ran = _native.launches() - before
+            for key in ("z", "ok", "conv_it", "post", "norm"):
+                assert np.array_equal(getattr(plain, key), getattr(fast, key)), (key, frames, start)
+            if frames == 1:
+                per_call = per_call or ran
+                assert ran == per_call > 12              # capture call and replays report the same kernel count
+    bits = dec.decode_batch(llr[:3], want_z=False, want_bits=True)
+    ref = dec.decode_batch(llr[:3], want_bits=True, replay=False)
+    assert np.array_equal(bits.zbits, ref.zbits) and np.array_equal(bits.ok, ref.ok)
+
+
 def test_early_termination_on_large_codes():
     """Config 3.  Frames leave the active set as soon as their syndrome vanishes (dynamic frame queue in
     the resident kernel, active-list compaction in the generic kernels); per-frame results must equal the
