@@ -361,13 +361,13 @@ def main():
         with open(peaks_path) as f:
             hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     alg_bytes = F * (n * 4 + n + 4 + 1)                     # LLRs in, z bytes + conv_it + ok out
-    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at 32768 frames
-    # (profiles/r1_ncu_final_kernel_summary.txt: 303.40 MB + 61.08 MB), scaled per frame
-    NCU_DRAM_BYTES_PER_FRAME = (303.404288e6 + 61.076736e6) / 32768
+    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at 131072 frames
+    # (this command, profiles/r1_ncu_final_kernel_summary.txt), scaled per frame
+    NCU_DRAM_BYTES_PER_FRAME = 11441.0      # profiles/r1_ncu_final_kernel_summary.txt: (1210.7 + 288.9) MB / 131072 frames
     roofline = {
         "bound": "sfu", "achieved": sfu_achieved / 1e9, "peak": mufu_peak / 1e9, "unit": "Gop/s",
         "frac": sfu_achieved / mufu_peak, "traffic": NCU_DRAM_BYTES_PER_FRAME * F,
-        "traffic_note": "HBM bytes per launch from the ncu capture in profiles/ (11.1 KB per frame; algorithmic 11.5 KB)",
+        "traffic_note": "HBM bytes per launch from the ncu capture in profiles/ (11.4 KB per frame; algorithmic 11.5 KB = 9216 B LLR row in + 2304 B decisions out + 4 B iteration)",
         "note": "resident kernel: messages never leave the SM, HBM is not the bound; achieved = 2 algorithmic "
                 "transcendentals per edge and pass / kernel time (CUDA events); peak = MUFU ex2 ops/s measured "
                 "in this run by ldpc_measure_mufu_peak; the kernel issues 3 MUFU per edge and pass, so "
