@@ -221,6 +221,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=131072, help="frames per step per GPU")
+    ap.add_argument("--spin", type=float, default=3.0, help="seconds of untimed load before the timed region (after the warm-up steps)")
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=0, help="cpu_baseline sample size (0 = 2048 x cores)")
     ap.add_argument("--workload", default="throughput", choices=["throughput", "parity576"],
@@ -296,10 +297,19 @@ def main():
     # ---- device-resident timing -------------------------------------------------------------------
     for _ in range(args.warmup):
         step_device()
-    t_spin = time.perf_counter()             # let the clocks settle: keep the GPU busy for >= 0.5 s before timing
-    while time.perf_counter() - t_spin < 0.5:
+    # let clocks and power state settle: keep the GPU busy for >= --spin seconds and until five consecutive steps run
+    # within 2 % of the fastest step seen (the first process on a fresh box can start 10 % slow), at most 5 s
+    t_spin = time.perf_counter()
+    best, recent = float("inf"), []
+    while True:
+        t_step = time.perf_counter()
         step_device()
         torch.cuda.synchronize()
+        recent = (recent + [time.perf_counter() - t_step])[-5:]
+        best = min(best, recent[-1])
+        spun = time.perf_counter() - t_spin
+        if spun >= max(5.0, args.spin) or (spun >= args.spin and len(recent) == 5 and max(recent) <= 1.02 * best):
+            break
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
