@@ -62,6 +62,7 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.rows = []
+        self.first = 0
         self.proc = None
 
     def start(self):
@@ -76,13 +77,17 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self):
+        """Forget what was sampled so far (warm-up); keep sampling."""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons, power = [], [], set(), []
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
             except (ValueError, IndexError):
@@ -221,7 +226,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=131072, help="frames per step per GPU")
-    ap.add_argument("--spin", type=float, default=3.0, help="seconds of untimed load before the timed region (after the warm-up steps)")
+    ap.add_argument("--spin", type=float, default=1.0, help="seconds of untimed load before the timed region (after the warm-up steps)")
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=0, help="cpu_baseline sample size (0 = 2048 x cores)")
     ap.add_argument("--workload", default="throughput", choices=["throughput", "parity576"],
@@ -297,8 +302,14 @@ def main():
     # ---- device-resident timing -------------------------------------------------------------------
     for _ in range(args.warmup):
         step_device()
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML attach) disturbs the GPU for a moment --
+    # started right at the timed region it made every step of that region ~12 % slower in about half of the
+    # runs (profiles/r1_tuning.md); its 100 ms polling afterwards does not.
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     # let clocks and power state settle: keep the GPU busy for >= --spin seconds and until five consecutive steps run
-    # within 2 % of the fastest step seen (the first process on a fresh box can start 10 % slow), at most 5 s
+    # within 2 % of the fastest step seen, at most 5 s
     t_spin = time.perf_counter()
     best, recent = float("inf"), []
     while True:
@@ -308,12 +319,13 @@ def main():
         recent = (recent + [time.perf_counter() - t_step])[-5:]
         best = min(best, recent[-1])
         spun = time.perf_counter() - t_spin
+        if os.environ.get("LDPC_BENCH_TRACE") and rank == 0:
+            print(f"warm-up t={spun:6.2f} s  step {recent[-1] * 1e3:7.3f} ms", file=sys.stderr)
         if spun >= max(5.0, args.spin) or (spun >= args.spin and len(recent) == 5 and max(recent) <= 1.02 * best):
             break
     barrier()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.mark()                       # samples from here on belong to the timed region
     launches0 = _native.launches()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
