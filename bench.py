@@ -300,11 +300,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing -------------------------------------------------------------------
+    out = None
     for _ in range(args.warmup):
-        step_device()
-    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML attach) disturbs the GPU for a moment --
-    # started right at the timed region it made every step of that region ~12 % slower in about half of the
-    # runs (profiles/r1_tuning.md); its 100 ms polling afterwards does not.
+        out = step_device()      # like the timed loop, keep the previous result alive while the next one is allocated
+    # nvidia-smi is started BEFORE the warm-up so that its start-up (NVML attach) is over when the timed
+    # region begins; only the samples taken during the timed region are kept.
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -314,7 +314,7 @@ def main():
     best, recent = float("inf"), []
     while True:
         t_step = time.perf_counter()
-        step_device()
+        out = step_device()
         torch.cuda.synchronize()
         recent = (recent + [time.perf_counter() - t_step])[-5:]
         best = min(best, recent[-1])
@@ -339,7 +339,10 @@ def main():
     launches = _native.launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e_beg.elapsed_time(e_end)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    kernel_ms = float(np.mean(step_ms))
+    if os.environ.get("LDPC_BENCH_TRACE") and rank == 0:
+        print("timed steps (ms): " + " ".join(f"{t:.2f}" for t in step_ms), file=sys.stderr)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
