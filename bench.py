@@ -160,7 +160,7 @@ def run_reference_arm(args):
                                    f"{cores} POSIX threads"},
         "e2e": {"value": value, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -216,11 +216,30 @@ def run_parity576(args):
                          "note": "whole step (check-node + variable-node + syndrome kernels x 20 passes), algorithmic bytes "
                                  "24E+26n per pass and frame in fp64 (three message sweeps); the check-node kernel is bound by "
                                  "fp64 tanh/atanh issue, not by HBM (ncu: FP64 pipe 44 %, issue slots 69 % busy)"}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE line on stdout.  Everything else a library prints (e.g. the NCCL version banner) goes to stderr:
+    main() points file descriptor 1 at stderr for the duration of the run and keeps the real stdout here."""
+    text = json.dumps(line) + "\n"
+    if _JSON_FD is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, text.encode())
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -429,7 +448,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
