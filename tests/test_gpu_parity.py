@@ -372,6 +372,70 @@ def test_tiny_host_calls_replayed_from_a_cuda_graph_give_the_same_results(name, 
     assert np.array_equal(bits.zbits, ref.zbits) and np.array_equal(bits.ok, ref.ok)
 
 
+def _random_qc(rng, z, mb, nb, max_deg):
+    """Random base matrix: every row has 2..max_deg circulants, every column block at least one."""
+    from scipy import sparse
+    shift = -np.ones((mb, nb), dtype=np.int16)
+    for a in range(mb):
+        cols = rng.choice(nb, size=int(rng.integers(2, min(max_deg, nb) + 1)), replace=False)
+        shift[a, cols] = rng.integers(0, z, size=cols.size)
+    for c in range(nb):
+        if (shift[:, c] < 0).all():
+            shift[int(rng.integers(0, mb)), c] = int(rng.integers(0, z))
+    rows, cols = [], []
+    for a in range(mb):
+        for c in range(nb):
+            if shift[a, c] >= 0:
+                r = np.arange(z)
+                rows.append(a * z + r)
+                cols.append(c * z + (r + shift[a, c]) % z)
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    h = sparse.csr_matrix((np.ones(rows.size, dtype=np.int32), (rows, cols)), shape=(mb * z, nb * z))
+    h.sort_indices()
+    return shift, h
+
+
+@pytest.mark.parametrize("seed,z,mb,nb,max_deg", [(1, 5, 2, 6, 4), (2, 17, 3, 9, 7), (3, 32, 6, 14, 5), (4, 40, 4, 12, 12),
+                                                  (5, 81, 5, 11, 6), (6, 64, 8, 16, 9), (7, 96, 2, 20, 20)])
+def test_run_time_specialised_kernel_on_random_base_matrices(seed, z, mb, nb, max_deg):
+    """Fuzz of csrc/qc_jit.cu + qc_kernel.cuh: random quasi-cyclic graphs (1..4 teams, empty team rows, z below,
+    at and above warp multiples, degree-2 rows, wide rows) against the fp64 oracle after one and two passes
+    (posteriors) and against oracle / generic fp32 kernels after 10 passes (decisions, syndrome, iteration)."""
+    import _native
+    rng = np.random.default_rng(seed)
+    shift, h = _random_qc(rng, z, mb, nb, max_deg)
+
+    class G:
+        n, m, row_ptr, col_idx = h.shape[1], h.shape[0], h.indptr.astype(np.int32), h.indices.astype(np.int32)
+        def csr(self):
+            return h
+    code = G()
+    dec = make_decoder(code, 10, "f32_fast")
+    assert dec.graph.is_qc and dec.graph.qc_z == z
+    assert dec.graph.prepare("f32_fast") == "qc_jit"
+    frames = 256
+    llr = awgn_llr(rng, frames, code.n, np.resize(np.array([0.0, 3.0, 6.0]), frames), rate=1.0 - mb / nb).astype(np.float32)
+    for passes in (1, 2):
+        got = dec.decode_batch(llr, want_posterior=True, max_iterations=passes)
+        want = oracle(code, llr.astype(np.float64), passes)
+        close = np.isclose(got.post, want["post"], rtol=2e-3, atol=2e-3)       # MUFU ex2 / lg2 approximations:
+        assert close.mean() > 0.9999                                            # a few saturated values (|L| ~ 35) are
+        np.testing.assert_allclose(got.post, want["post"], rtol=1e-2, atol=1e-2)   # off by up to 3e-3 relative
+        assert (got.z == want["z"]).mean() > 0.9999 and np.array_equal(got.ok, want["ok"])
+    for fix in (False, True):
+        d = make_decoder(code, 10, "f32_fast", fix_odd_check_sign=fix)
+        got = d.decode_batch(llr)
+        gen = make_decoder(code, 10, "f32", fix_odd_check_sign=fix).decode_batch(llr)
+        assert (got.z == gen.z).mean() > 0.998 and (got.ok == gen.ok).mean() > 0.97
+        if not fix:
+            want = oracle(code, llr.astype(np.float64), 10)
+            assert (got.z == want["z"]).mean() > 0.998 and (got.ok == want["ok"]).mean() > 0.97
+            both = (got.ok == 1) & (want["ok"] == 1)
+            assert not both.any() or (got.conv_it[both] == want["conv_it"][both]).mean() > 0.95
+    fixed = dec.decode_batch(llr, early_termination=False)
+    assert fixed.z.shape == (frames, code.n) and set(np.unique(fixed.ok)) <= {0, 1}
+
+
 def test_early_termination_on_large_codes():
     """Config 3.  Frames leave the active set as soon as their syndrome vanishes (dynamic frame queue in
     the resident kernel, active-list compaction in the generic kernels); per-frame results must equal the
