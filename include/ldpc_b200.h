@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define LDPC_B200_ABI_VERSION 1
+#define LDPC_B200_ABI_VERSION 2
 
 typedef enum ldpc_status {
     LDPC_OK = 0,

@@ -18,7 +18,7 @@ FLAG_EARLY_TERM, FLAG_COMPACT, FLAG_FIX_ODD_SIGN, FLAG_FORCE_GENERIC, FLAG_TABLE
 FLAG_NORM_LLR, FLAG_NO_REPLAY = 0x40, 0x80
 CHANNEL_SIGMA_SQ, CHANNEL_AMP_07 = 0x1, 0x2
 KERNEL_KINDS = ("generic", "qc_table", "qc_registered", "qc_jit")      # ldpc_kernel_kind
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = [
     "ldpc_host_edge_index", "ldpc_host_detect_qc", "ldpc_host_standard_form",
