@@ -76,6 +76,8 @@ struct ldpc_graph {
     void* d_qc_tables = nullptr;
     int device = -1;
     uint64_t serial = 0;            // unique per handle (keys of caches that must not alias a freed pointer)
+    // kernel family per (TABLE_KERNEL, NO_JIT) flag combination, -1 = not determined yet (qc_resident_kind)
+    mutable std::atomic<int> kind_cache[4] = {{-1}, {-1}, {-1}, {-1}};
 };
 
 namespace ldpc {

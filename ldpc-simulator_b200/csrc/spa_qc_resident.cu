@@ -446,11 +446,16 @@ int qc_resident_decode(const ldpc_graph* g, int64_t frames, int max_iter, unsign
 int qc_resident_kind(const ldpc_graph* g, unsigned flags)
 {
     if (!g || !g->is_qc) return LDPC_KERNEL_GENERIC;
+    std::atomic<int>& memo = g->kind_cache[((flags & LDPC_FLAG_TABLE_KERNEL) ? 1 : 0) | ((flags & LDPC_FLAG_NO_JIT) ? 2 : 0)];
+    int kind = memo.load(std::memory_order_relaxed);
+    if (kind >= 0) return kind;                       // asked on every decode call: decided once per handle
     const bool table = qc_resident_supported(g);
-    if (flags & LDPC_FLAG_TABLE_KERNEL) return table ? LDPC_KERNEL_QC_TABLE : LDPC_KERNEL_GENERIC;
-    if (qc_spec_find(g) >= 0) return LDPC_KERNEL_QC_REGISTERED;
-    if (!(flags & LDPC_FLAG_NO_JIT) && qc_jit_supported(g)) return LDPC_KERNEL_QC_JIT;
-    return table ? LDPC_KERNEL_QC_TABLE : LDPC_KERNEL_GENERIC;
+    if (flags & LDPC_FLAG_TABLE_KERNEL) kind = table ? LDPC_KERNEL_QC_TABLE : LDPC_KERNEL_GENERIC;
+    else if (qc_spec_find(g) >= 0) kind = LDPC_KERNEL_QC_REGISTERED;
+    else if (!(flags & LDPC_FLAG_NO_JIT) && qc_jit_supported(g)) kind = LDPC_KERNEL_QC_JIT;
+    else kind = table ? LDPC_KERNEL_QC_TABLE : LDPC_KERNEL_GENERIC;
+    memo.store(kind, std::memory_order_relaxed);
+    return kind;
 }
 
 void qc_resident_release(ldpc_graph* g)
