@@ -135,6 +135,10 @@ def build_parser():
     p.add_argument("--normalized-llr", action="store_true")
     p.add_argument("--encoding-method", "-e", type=str, choices=["standard", "richardson-urbanke"], default="standard")
     p.add_argument("--threads", "-t", type=int, default=1)
+    p.add_argument("--s-param", type=int, default=2, help="S of the S-random interleaver (recorded only)")
+    p.add_argument("--ru-gap", type=int, default=None, help="accepted for compatibility; the Richardson-Urbanke encoder is out of scope")
+    p.add_argument("--plot", action="store_true", help="accepted for compatibility: plot the written results with the reference's plot_results.py")
+    p.add_argument("--plot-save", type=str, default=None)
     p.add_argument("--adaptive", action="store_true")
     p.add_argument("--adaptive-strategy", type=str, choices=["threshold"], default="threshold")
     p.add_argument("--matrix-dir", type=str, default=None)
@@ -165,6 +169,8 @@ def main(argv=None):
     st.set_decoder_type(LDPCDecoderType.SUM_PRODUCT)
     st.set_interleaver_type({"none": InterleaverType.NONE, "regular": InterleaverType.REGULAR,
                              "random": InterleaverType.RANDOM, "srandom": InterleaverType.SRANDOM}[args.interleaver])
+    if args.interleaver == "srandom":
+        st.set_s_param(args.s_param)
     st.set_ber_calculate(args.ber)
     st.set_fer_calculate(args.fer)
     st.set_normalized_llr_calculate(args.normalized_llr)
@@ -180,6 +186,9 @@ def main(argv=None):
         result = AdaptiveController(strategy, MatrixCatalog(matrix_dir)).run_adaptive_sweep(edd, st, args, method)
     else:
         result = run_simulation(edd, st, args, method)
+    if args.plot or args.plot_save:
+        print("note: plots are not drawn here; feed the results file to the reference's plot_results.py / visualization.py "
+              "(the JSON / CSV written by --output-json / --output-csv is byte-compatible)")
     if args.output_json:
         result.to_json(args.output_json)
     if args.output_csv:
