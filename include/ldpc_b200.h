@@ -52,7 +52,9 @@ typedef enum ldpc_status {
 typedef enum ldpc_dtype {
     LDPC_F64 = 0,      /* parity mode: the reference's fp64 formulas literally (spa_decoder.py:133-168) */
     LDPC_F32 = 1,      /* same formulas in fp32 with accurate tanhf/atanhf, any graph */
-    LDPC_F32_FAST = 2  /* throughput mode: SM-resident quasi-cyclic kernel, fp32 with MUFU approximations */
+    LDPC_F32_FAST = 2  /* throughput mode, fp32 with MUFU approximations: the SM-resident kernel on quasi-cyclic
+                          graphs, the generic kernels on every other graph (with a MUFU check node when no
+                          check has more than 24 edges, else identical to LDPC_F32) */
 } ldpc_dtype;
 
 /* Flags for ldpc_decode_batch / ldpc_mc_run. */

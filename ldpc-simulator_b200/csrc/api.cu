@@ -118,13 +118,10 @@ int decode_device(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, 
         return qc_resident_decode(g, frames, max_iter, flags, (const float*)llr, z, zbits, conv, ok,
                                   (float*)post, mc, ws, ws_bytes, stream);
     }
-    if (dtype == LDPC_F32_FAST && !(flags & LDPC_FLAG_FORCE_GENERIC) && !norm) {
-        set_error("LDPC_F32_FAST needs a quasi-cyclic graph supported by the resident kernel; "
-                  "use LDPC_F32 (or LDPC_FLAG_FORCE_GENERIC) for this graph");
-        return LDPC_ERR_UNSUPPORTED;
-    }
+    // LDPC_F32_FAST on a graph without a resident kernel (or with LDPC_FLAG_FORCE_GENERIC): the generic
+    // kernels with MUFU arithmetic in the check node
     if (!z) { set_error("the generic path needs z_dev"); return LDPC_ERR_INVALID; }
-    int rc = generic_decode(g, dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32, frames, max_iter, flags, llr, z, conv, ok,
+    int rc = generic_decode(g, dtype, frames, max_iter, flags, llr, z, conv, ok,
                             post, norm, k_info, ws, ws_bytes, stream);
     if (rc) return rc;
     if (zbits) {
@@ -440,10 +437,6 @@ extern "C" int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int m
         return qc_resident_decode(g, frames, max_iter, flags, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                   mc, workspace_dev, workspace_bytes, stream);
     }
-    if (dtype == LDPC_F32_FAST && !(flags & LDPC_FLAG_FORCE_GENERIC) && !want_norm) {
-        set_error("LDPC_F32_FAST needs a quasi-cyclic graph supported by the resident kernel");
-        return LDPC_ERR_UNSUPPORTED;
-    }
     // generic path: generate -> decode -> count, chunked to the workspace
     const int gd = dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32;
     const size_t esz = gd == LDPC_F64 ? 8 : 4;
@@ -471,7 +464,8 @@ extern "C" int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int m
         rc = channel_fill(n, gd, c, speed, snr_db, sigma_sq_quirk, seed, stream_id, frame_offset + (uint64_t)f0,
                           codeword_dev ? codeword_dev + f0 * codeword_stride : nullptr, codeword_stride, llr, stream);
         if (rc) return rc;
-        rc = generic_decode(g, gd, c, max_iter, flags, llr, z, conv, ok, nullptr, norm, k_info, p, ws_bytes, stream);
+        rc = generic_decode(g, dtype == LDPC_F32_FAST ? LDPC_F32_FAST : gd, c, max_iter, flags, llr, z, conv, ok, nullptr, norm, k_info,
+                            p, ws_bytes, stream);
         if (rc) return rc;
         rc = count_errors(n, k_info, c, z, ok, conv, codeword_dev ? codeword_dev + f0 * codeword_stride : nullptr, codeword_stride,
                           info_mask_dev, norm, k_info, (unsigned long long*)counters_dev, stream);

@@ -40,17 +40,18 @@ def main():
         k = code.n - code.m
         frames = max(4096, min(262144, (256 << 20) // (4 * code.n)))
         llr = Channel.create_channel(k / code.n, 2.0, 0.0, 1, 0.1, 1).device_llr(frames, code.n, seed=1)
-        variants = [("specialised", dict()), ("table", dict(jit=False, table_kernel=True)), ("generic_f32", dict(force_generic=True))]
+        variants = [("specialised", dict()), ("table", dict(jit=False, table_kernel=True)),
+                    ("generic_f32_fast", dict(force_generic=True)), ("generic_f32", dict(force_generic=True, precision="f32"))]
         for label, kw in variants:
             flags = (_native.FLAG_TABLE_KERNEL | _native.FLAG_NO_JIT) if label == "table" else \
-                    (_native.FLAG_FORCE_GENERIC if label == "generic_f32" else 0)
+                    (_native.FLAG_FORCE_GENERIC if label.startswith("generic") else 0)
             family = dec.graph.prepare("f32_fast", flags)
             if label == "table" and family != "qc_table":
                 print(json.dumps({"code": name, "variant": label, "family": None, "note": "no table-driven shape for this base matrix"}))
                 continue
-            f = frames if label != "generic_f32" else min(frames, 32768)
+            f = frames if not label.startswith("generic") else min(frames, 32768)
             x = llr[:f]
-            ws = torch.empty(max(256, int(_native.lib().ldpc_workspace_bytes(dec.graph.handle, f, 1 if label == "generic_f32" else 2))),
+            ws = torch.empty(max(256, int(_native.lib().ldpc_workspace_bytes(dec.graph.handle, f, 1 if label.startswith("generic") else 2))),
                              dtype=torch.uint8, device="cuda")
             run = lambda: dec.decode_batch_device(x, early_termination=False, workspace=ws, **kw)
             for _ in range(2):
