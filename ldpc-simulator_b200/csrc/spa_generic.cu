@@ -131,6 +131,8 @@ struct ChunkState {
                           //     fills slot (p+1)%3 and clears slot (p+2)%3
     uint8_t* failed;      // [Fc] some check unsatisfied in this pass
     uint8_t* done;        // [Fc] frame finished (converged)
+    uint8_t* keep;        // [Fc] slot stays in the active list (compaction only)
+    int32_t* removed;     // frames that left the active list in this pass (compaction only)
     int32_t* norm_cnt;    // [Fc] sign changes of the metric in this pass
 };
 
@@ -171,6 +173,7 @@ __global__ void k_init_chunk(ChunkState st, int Fc, int64_t valid)
         st.count[0] = (int)valid;
         st.count[1] = 0;
         st.count[2] = 0;
+        *st.removed = 0;
     }
 }
 
@@ -503,6 +506,32 @@ k_finish_pass(ChunkState st, int pass, int last_pass, int early_term, int compac
             if (t == 0) *next_count = count;
             continue;
         }
+        // compaction: only mark here; k_compact_list rebuilds the list -- and leaves it untouched when no frame left
+        // in this pass, because every rebuild appends the warps' survivors in atomic order and so moves frames
+        // off the 128-byte lines of their neighbours
+        if (t < count) st.keep[t] = keep ? 1 : 0;
+        const unsigned gone = __ballot_sync(0xffffffffu, t < count && !keep);
+        if (lane == 0 && gone) atomicAdd(st.removed, __popc(gone));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_compact_list(ChunkState st, int pass)
+{
+    const int count = st.count[pass % 3];
+    const int32_t* cur = st.active[pass & 1];
+    int32_t* nxt = st.active[(pass & 1) ^ 1];
+    int32_t* next_count = st.count + (pass + 1) % 3;
+    const int removed = *st.removed;
+    const unsigned lane = threadIdx.x & 31;
+    const int cpad = (count + 31) & ~31;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cpad; t += gridDim.x * blockDim.x) {
+        if (removed == 0) {
+            if (t < count) nxt[t] = cur[t];
+            if (t == 0) *next_count = count;
+            continue;
+        }
+        const bool keep = t < count && st.keep[t];
         const unsigned mask = __ballot_sync(0xffffffffu, keep);
         int base = 0;
         if (lane == 0 && mask) base = atomicAdd(next_count, __popc(mask));
@@ -510,6 +539,9 @@ k_finish_pass(ChunkState st, int pass, int last_pass, int early_term, int compac
         if (keep) nxt[base + __popc(mask & ((1u << lane) - 1u))] = cur[t];
     }
 }
+
+// clears the removed-frames counter after k_compact_list has read it (next pass accumulates again)
+__global__ void k_clear_removed(ChunkState st) { *st.removed = 0; }
 
 // zb/post [n][Fc] frame-minor -> z_out/post_out [F][n] row-major.
 template <typename T>
@@ -563,7 +595,7 @@ size_t bytes_per_chunk(const ldpc_graph* g, int64_t Fc)
     b += align_up(sizeof(T) * (size_t)g->n * Fc, 256);        // post
     b += align_up((size_t)g->n * Fc, 256);                    // zb
     b += align_up(sizeof(int32_t) * (size_t)Fc, 256) * 3;     // active x2, norm_cnt
-    b += align_up((size_t)Fc, 256) * 2;                       // failed, done
+    b += align_up((size_t)Fc, 256) * 3;                       // failed, done, keep
     b += 256;                                                 // counts
     return b;
 }
@@ -602,7 +634,9 @@ int decode_typed(const ldpc_graph* g, int64_t F, int max_iter, unsigned flags, c
     st.norm_cnt = (int32_t*)take(sizeof(int32_t) * (size_t)Fc);
     st.failed = (uint8_t*)take((size_t)Fc);
     st.done = (uint8_t*)take((size_t)Fc);
+    st.keep = (uint8_t*)take((size_t)Fc);
     st.count = (int32_t*)take(256);
+    st.removed = st.count + 8;
 
     const int early = (flags & LDPC_FLAG_EARLY_TERM) ? 1 : 0;
     const int compact = (flags & LDPC_FLAG_COMPACT) ? 1 : 0;
@@ -678,6 +712,12 @@ int decode_typed(const ldpc_graph* g, int64_t F, int max_iter, unsigned flags, c
             k_finish_pass<<<std::min((Fci + kThreads - 1) / kThreads, grid_cap), kThreads, 0, stream>>>(
                 st, it, last, early, compact, conv_out + f0, ok_out + f0, norm_out ? norm_out + f0 : nullptr, k_norm);
             LDPC_LAUNCH_CHECK();
+            if (compact) {
+                k_compact_list<<<std::min((Fci + kThreads - 1) / kThreads, grid_cap), kThreads, 0, stream>>>(st, it);
+                LDPC_LAUNCH_CHECK();
+                k_clear_removed<<<1, 1, 0, stream>>>(st);
+                LDPC_LAUNCH_CHECK();
+            }
         }
         const int64_t tiles = (int64_t)((g->n + 31) / 32) * (Fc / 32);
         k_store_out<T><<<(int)std::min<int64_t>(tiles, grid_cap * 4), dim3(32, 8), 0, stream>>>(

@@ -72,6 +72,12 @@ def main():
         ms = timed(lambda: d83.decode_batch_device(l83, early_termination=early, compact=compact))
         out.append(dict(scenario=f"generic f32 wimax-2304-0.83 4.5 dB 16384 frames early={early} compact={compact}", ms=round(ms, 2),
                         converged=round(float(res.ok.float().mean()), 3), mean_it=round(float(res.conv_it[res.conv_it >= 0].float().mean()), 2)))
+    # 3b. compaction when nothing converges and the frame count is ragged: must cost nothing
+    lo = Channel.create_channel(0.5, 1.0, 0.0, 1, 0.1, 1).device_llr(29127, code.n, seed=4)
+    dgen = decoder(code, "f32")
+    for compact in (False, True):
+        ms = timed(lambda: dgen.decode_batch_device(lo, early_termination=True, compact=compact, force_generic=True))
+        out.append(dict(scenario=f"generic f32 wimax-2304 1 dB 29127 frames (none converge) compact={compact}", ms=round(ms, 2)))
     # 4. Monte-Carlo on H_std in fp64 with the reference's kind of block counts
     edd = EncoderDecoderData(h=load_code("wimax_576_0.5").sparse_matrix())
     eng = MonteCarloEngine(edd, graph="std", precision="f64", max_iterations=20, seed=5)
