@@ -95,9 +95,15 @@ void staging_copy(void* dst, const void* src, size_t bytes)
     if (want < 2) { memcpy(dst, src, bytes); return; }
     std::vector<std::thread> pool;
     const size_t part = (bytes / want + 4095) & ~(size_t)4095;
-    for (size_t off = part; off < bytes; off += part)
-        pool.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, std::min(part, bytes - off)); });
+    size_t off = part;
+    try {
+        for (; off < bytes; off += part)
+            pool.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, std::min(part, bytes - off)); });
+    } catch (...) {
+        // no more threads to be had: this thread copies the rest (no exception may cross the C ABI)
+    }
     memcpy(dst, src, std::min(part, bytes));
+    if (off < bytes) memcpy((char*)dst + off, (const char*)src + off, bytes - off);
     for (auto& t : pool) t.join();
 }
 
