@@ -116,3 +116,24 @@ def test_jit_rejects_what_the_kernel_cannot_run():
     assert rc == -1 and b"out of range" in lib.ldpc_last_error()
     rc, _, _ = _jit(8, np.array([[0, -1], [1, -1]]), compile_it=True)     # degree-1 checks, empty column block
     assert rc == -4
+
+
+def test_the_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under ldpc-simulator_b200/ (the package, its CUDA sources, the
+    build recipe) may import, link or execute it; only tests/, bench.py's CPU arms and smoke() do."""
+    pkg = os.path.join(REPO, "ldpc-simulator_b200")
+    offenders = []
+    for root, _dirs, files in os.walk(pkg):
+        if os.path.basename(root) in ("build", "lib", "__pycache__"):
+            continue
+        for name in files:
+            if not name.endswith((".py", ".cu", ".cuh", ".json")) or name == "qc_jit_src_gen.cuh":
+                continue
+            text = open(os.path.join(root, name), encoding="utf-8", errors="replace").read()
+            for line in text.splitlines():
+                code = line.split("#")[0].split("//")[0]
+                if re.search(r"\boracle\b", code) or "spa_oracle" in code:
+                    offenders.append((name, line.strip()))
+    assert not offenders, offenders
+    shared = open(_native.LIB_PATH, "rb").read()
+    assert b"spa_oracle" not in shared
