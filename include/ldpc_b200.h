@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define LDPC_B200_ABI_VERSION 2
+#define LDPC_B200_ABI_VERSION 3
 
 typedef enum ldpc_status {
     LDPC_OK = 0,
@@ -240,6 +240,32 @@ int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, un
                 uint64_t seed, uint32_t stream_id, uint64_t frame_offset,
                 const uint8_t* codeword_dev, int64_t codeword_stride, const uint8_t* info_mask_dev, int k_info,
                 uint64_t* counters_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/*
+ * The channel of Channel.create_channel(speed, sn1, sn2, mode, p, mod) (channel.py:102-125) for the device generator.
+ * mode 1: AWGN; mode 2: AWGN + interference in a share p of the band (every bit is hit with probability
+ * P(a/n < p), a uniform in 0..n-1, :86-96); mode 3: AWGN + counter interference weighted with p (:98-100).
+ * The Gaussian terms come from Philox, not from the reference's Park-Miller generators: same distribution,
+ * not the same numbers (the host-side Channel.process reproduces the reference's stream bit for bit).
+ */
+typedef struct ldpc_channel {
+    int mode;                    /* 1, 2 or 3 */
+    int modulation;              /* 1: symbols +-1, 2: +-0.7 (channel.py:49-51) */
+    int sigma_sq_quirk;          /* mode 1 only: noise deviation sigma^2 as in the reference (channel.py:68) */
+    double speed;                /* plays the role of the code rate in sigma (channel.py:113) */
+    double snr_db;               /* sn1 */
+    double interference_snr_db;  /* sn2, modes 2 and 3 */
+    double p;                    /* modes 2 and 3 */
+} ldpc_channel;
+
+/* ldpc_mc_run / ldpc_channel_llr with a full channel description. */
+int ldpc_mc_run_ex(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
+                   const ldpc_channel* channel, uint64_t seed, uint32_t stream_id, uint64_t frame_offset,
+                   const uint8_t* codeword_dev, int64_t codeword_stride, const uint8_t* info_mask_dev, int k_info,
+                   uint64_t* counters_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+int ldpc_channel_llr_ex(int n, int dtype, int64_t frames, const ldpc_channel* channel,
+                        uint64_t seed, uint32_t stream_id, uint64_t frame_offset,
+                        const uint8_t* codeword_dev, int64_t codeword_stride, void* llr_dev, void* stream);
 
 /* Workspace for ldpc_mc_run (it also holds the generated LLRs and decoder outputs). */
 size_t ldpc_mc_workspace_bytes(const ldpc_graph* g, int64_t frames, int dtype);

@@ -18,17 +18,23 @@ FLAG_EARLY_TERM, FLAG_COMPACT, FLAG_FIX_ODD_SIGN, FLAG_FORCE_GENERIC, FLAG_TABLE
 FLAG_NORM_LLR, FLAG_NO_REPLAY = 0x40, 0x80
 CHANNEL_SIGMA_SQ, CHANNEL_AMP_07 = 0x1, 0x2
 KERNEL_KINDS = ("generic", "qc_table", "qc_registered", "qc_jit")      # ldpc_kernel_kind
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = [
     "ldpc_host_edge_index", "ldpc_host_detect_qc", "ldpc_host_standard_form",
     "ldpc_graph_create_csr", "ldpc_graph_create_qc", "ldpc_graph_info", "ldpc_graph_qc_shifts",
     "ldpc_graph_prepare", "ldpc_host_jit_compile",
     "ldpc_graph_destroy", "ldpc_workspace_bytes", "ldpc_decode_batch", "ldpc_decode_batch_host",
-    "ldpc_mc_run", "ldpc_mc_workspace_bytes", "ldpc_channel_llr", "ldpc_encoder_create", "ldpc_encoder_destroy",
+    "ldpc_mc_run", "ldpc_mc_run_ex", "ldpc_mc_workspace_bytes", "ldpc_channel_llr", "ldpc_channel_llr_ex", "ldpc_encoder_create", "ldpc_encoder_destroy",
     "ldpc_encode_batch", "ldpc_kernel_launch_count",
     "ldpc_measure_mufu_peak", "ldpc_last_error", "ldpc_abi_version",
 ]
+
+
+class ChannelDesc(C.Structure):
+    """struct ldpc_channel (include/ldpc_b200.h)."""
+    _fields_ = [("mode", C.c_int), ("modulation", C.c_int), ("sigma_sq_quirk", C.c_int), ("speed", C.c_double),
+                ("snr_db", C.c_double), ("interference_snr_db", C.c_double), ("p", C.c_double)]
 
 
 class NativeLibraryError(RuntimeError):
@@ -78,6 +84,10 @@ def lib():
         "ldpc_decode_batch_host": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_uint, vp, vp, vp, vp, vp, vp, vp, C.c_int]),
         "ldpc_mc_run": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_uint, C.c_double, C.c_double, C.c_int,
                                   C.c_uint64, C.c_uint32, C.c_uint64, vp, i64, vp, C.c_int, vp, vp, C.c_size_t, vp]),
+        "ldpc_mc_run_ex": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_uint, C.POINTER(ChannelDesc),
+                                     C.c_uint64, C.c_uint32, C.c_uint64, vp, i64, vp, C.c_int, vp, vp, C.c_size_t, vp]),
+        "ldpc_channel_llr_ex": (C.c_int, [C.c_int, C.c_int, i64, C.POINTER(ChannelDesc), C.c_uint64,
+                                          C.c_uint32, C.c_uint64, vp, i64, vp, vp]),
         "ldpc_mc_workspace_bytes": (C.c_size_t, [vp, i64, C.c_int]),
         "ldpc_channel_llr": (C.c_int, [C.c_int, C.c_int, i64, C.c_double, C.c_double, C.c_int, C.c_uint64,
                                        C.c_uint32, C.c_uint64, vp, i64, vp, vp]),

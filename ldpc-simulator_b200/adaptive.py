@@ -140,7 +140,8 @@ class AdaptiveController:
                 sigma_sq_quirk=not getattr(args, "no_sigma_sq_quirk", False),
                 seed=seed if seed is not None else int(time.time() * 1e6) % (2 ** 63),
                 normalized_llr=bool(getattr(args, "normalized_llr", False)),
-                modulation=state.current_modulation)
+                modulation=state.current_modulation, mode=getattr(args, "mode", 1), p=getattr(args, "p", 0.1),
+                interference_snr=getattr(args, "interference_snr", 0.0) if getattr(args, "mode", 1) != 1 else 0.0)
         return self._engines[key]
 
     # ---- the sweep ---------------------------------------------------------------------------

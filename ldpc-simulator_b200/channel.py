@@ -24,6 +24,7 @@ import time
 
 import numpy as np
 
+import _native
 from constants import IDUM1, IDUM2
 from generator import Generator
 
@@ -43,7 +44,14 @@ class Channel:
 
     def _require_awgn(self):
         if self.mode != 1:
-            raise NotImplementedError("only mode 1 (AWGN) is vectorised / on the GPU; modes 2 and 3 go through process()")
+            raise NotImplementedError("process_batch covers mode 1 (AWGN); modes 2 and 3 go through process() or device_llr()")
+
+    def describe(self, speed=None, snr_db=None):
+        """The ``ldpc_channel`` struct of this channel for the device generator."""
+        return _native.ChannelDesc(
+            int(self.mode), int(self.modulation), int(bool(self.sigma_sq_quirk)),
+            float(self._speed if speed is None else speed), float(self._snr_db if snr_db is None else snr_db),
+            float(getattr(self, "_snr2_db", 0.0)), float(self.p))
 
     @property
     def amplitude(self):
@@ -93,9 +101,7 @@ class Channel:
         import ctypes as C
         import torch
         import _native
-        self._require_awgn()
-        if speed is None or snr_db is None:
-            speed, snr_db = self._speed, self._snr_db
+        desc = self.describe(speed, snr_db)
         tdt = torch.float64 if dtype == "f64" else torch.float32
         out = torch.empty((frames, n), dtype=tdt, device="cuda")
         cw, stride = None, 0
@@ -106,9 +112,8 @@ class Channel:
                 if tuple(cw.shape) != (frames, n):
                     raise ValueError(f"per-frame codewords must be [{frames}, {n}]")
                 stride = n
-        _native.check(_native.lib().ldpc_channel_llr(
-            n, _native.LDPC_F64 if dtype == "f64" else _native.LDPC_F32, frames, float(speed), float(snr_db),
-            int(bool(self.sigma_sq_quirk)) | (_native.CHANNEL_AMP_07 if self.modulation == 2 else 0),
+        _native.check(_native.lib().ldpc_channel_llr_ex(
+            n, _native.LDPC_F64 if dtype == "f64" else _native.LDPC_F32, frames, C.byref(desc),
             int(seed), int(stream_id), int(frame_offset),
             cw.data_ptr() if cw is not None else None, stride, out.data_ptr(),
             torch.cuda.current_stream().cuda_stream))
@@ -133,5 +138,5 @@ class Channel:
         ch = Channel(mode, p, mod, L_c1, L_c2, L_c3)
         ch.gen_ptr = Generator(IDUM1, sigma1)
         ch.gen_ptr2 = Generator(IDUM2, sigma2)
-        ch._speed, ch._snr_db = speed, sn1
+        ch._speed, ch._snr_db, ch._snr2_db = speed, sn1, sn2
         return ch

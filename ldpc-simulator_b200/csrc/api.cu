@@ -431,6 +431,16 @@ extern "C" size_t ldpc_mc_workspace_bytes(const ldpc_graph* g, int64_t frames, i
            align_up((size_t)F, 256) + generic_workspace_bytes(g, F, dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32);
 }
 
+static ldpc_channel awgn_channel(double speed, double snr_db, int channel_flags)
+{
+    ldpc_channel ch;
+    ch.mode = 1;
+    ch.modulation = (channel_flags & LDPC_CHANNEL_AMP_07) ? 2 : 1;
+    ch.sigma_sq_quirk = (channel_flags & LDPC_CHANNEL_SIGMA_SQ) ? 1 : 0;
+    ch.speed = speed; ch.snr_db = snr_db; ch.interference_snr_db = 0.0; ch.p = 0.0;
+    return ch;
+}
+
 extern "C" int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
                            double speed, double snr_db, int sigma_sq_quirk,
                            uint64_t seed, uint32_t stream_id, uint64_t frame_offset,
@@ -438,10 +448,21 @@ extern "C" int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int m
                            int k_info, uint64_t* counters_dev, void* workspace_dev, size_t workspace_bytes,
                            void* stream_v)
 {
+    const ldpc_channel ch = awgn_channel(speed, snr_db, sigma_sq_quirk);
+    return ldpc_mc_run_ex(g, dtype, frames, max_iter, flags, &ch, seed, stream_id, frame_offset, codeword_dev, codeword_stride,
+                          info_mask_dev, k_info, counters_dev, workspace_dev, workspace_bytes, stream_v);
+}
+
+extern "C" int ldpc_mc_run_ex(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
+                              const ldpc_channel* channel, uint64_t seed, uint32_t stream_id, uint64_t frame_offset,
+                              const uint8_t* codeword_dev, int64_t codeword_stride, const uint8_t* info_mask_dev,
+                              int k_info, uint64_t* counters_dev, void* workspace_dev, size_t workspace_bytes,
+                              void* stream_v)
+{
     int rc = check_common(g, dtype, frames, max_iter);
     if (rc) return rc;
     if (!counters_dev) { set_error("null counters"); return LDPC_ERR_INVALID; }
-    if (!(speed > 0.0)) { set_error("speed must be positive"); return LDPC_ERR_INVALID; }
+    if (!channel) { set_error("null channel"); return LDPC_ERR_INVALID; }
     if (k_info < 0 || k_info > g->n) { set_error("k_info out of range"); return LDPC_ERR_INVALID; }
     if (codeword_stride != 0 && codeword_stride < g->n) { set_error("codeword_stride must be 0 or >= n"); return LDPC_ERR_INVALID; }
     if (frames == 0) return LDPC_OK;
@@ -450,7 +471,7 @@ extern "C" int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int m
     if (!want_norm && use_resident(g, dtype, flags)) {
         McParams mc;
         mc.active = true;
-        channel_params(speed, snr_db, sigma_sq_quirk, seed, stream_id, &mc);
+        if ((rc = channel_params(*channel, g->n, seed, stream_id, &mc))) return rc;
         mc.frame_offset = frame_offset;
         mc.codeword = codeword_dev;
         mc.codeword_stride = codeword_stride;
@@ -484,7 +505,7 @@ extern "C" int ldpc_mc_run(const ldpc_graph* g, int dtype, int64_t frames, int m
     const size_t ws_bytes = workspace_bytes - (size_t)(p - (char*)workspace_dev);
     for (int64_t f0 = 0; f0 < frames; f0 += chunk) {
         const int64_t c = std::min<int64_t>(chunk, frames - f0);
-        rc = channel_fill(n, gd, c, speed, snr_db, sigma_sq_quirk, seed, stream_id, frame_offset + (uint64_t)f0,
+        rc = channel_fill(n, gd, c, *channel, seed, stream_id, frame_offset + (uint64_t)f0,
                           codeword_dev ? codeword_dev + f0 * codeword_stride : nullptr, codeword_stride, llr, stream);
         if (rc) return rc;
         rc = generic_decode(g, dtype == LDPC_F32_FAST ? LDPC_F32_FAST : gd, c, max_iter, flags, llr, z, conv, ok, nullptr, norm, k_info,
@@ -501,7 +522,16 @@ extern "C" int ldpc_channel_llr(int n, int dtype, int64_t frames, double speed, 
                                 uint64_t seed, uint32_t stream_id, uint64_t frame_offset,
                                 const uint8_t* codeword_dev, int64_t codeword_stride, void* llr_dev, void* stream)
 {
-    return channel_fill(n, dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32, frames, speed, snr_db, sigma_sq_quirk, seed,
+    const ldpc_channel ch = awgn_channel(speed, snr_db, sigma_sq_quirk);
+    return ldpc_channel_llr_ex(n, dtype, frames, &ch, seed, stream_id, frame_offset, codeword_dev, codeword_stride, llr_dev, stream);
+}
+
+extern "C" int ldpc_channel_llr_ex(int n, int dtype, int64_t frames, const ldpc_channel* channel,
+                                   uint64_t seed, uint32_t stream_id, uint64_t frame_offset,
+                                   const uint8_t* codeword_dev, int64_t codeword_stride, void* llr_dev, void* stream)
+{
+    if (!channel) { set_error("null channel"); return LDPC_ERR_INVALID; }
+    return channel_fill(n, dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32, frames, *channel, seed,
                         stream_id, frame_offset, codeword_dev, codeword_stride, llr_dev, (cudaStream_t)stream);
 }
 

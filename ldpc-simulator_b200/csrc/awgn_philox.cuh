@@ -55,6 +55,10 @@ struct ChannelConst {
     float noise_dev;   // sigma^2 (quirk) or sigma
     float llr_scale;   // 2 / sigma^2
     float amp;         // symbol amplitude: 1 (modulation 1, :49) or 0.7 (modulation 2, :51)
+    // interference (channel modes 2 and 3, :83-100); a2 = 0 and hit_threshold = 0 in mode 1
+    float a2;          // deviation of the second noise term when the bit is hit
+    float l_hit;       // LLR scale of a hit bit (L_c2 / L_c3); llr_scale is the scale of the others (L_c1)
+    uint32_t hit_threshold;   // a bit is hit iff a uniform 32-bit draw is below this (0xffffffff = always)
     uint32_t k0, k1;   // Philox key = seed
     uint32_t stream_id;
 };
@@ -68,11 +72,30 @@ __device__ __forceinline__ void channel_llr4(const ChannelConst& cc, uint64_t fr
     float g[4];
     box_muller(p.x, p.y, g[0], g[1]);
     box_muller(p.z, p.w, g[2], g[3]);
+    if (cc.hit_threshold == 0u) {                          // mode 1: AWGN only
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float sym = ((bits4 >> i) & 1u) ? cc.amp : -cc.amp;
+            const float y = __fmaf_rn(cc.noise_dev, g[i], sym);
+            out[i] = __fmul_rn(y, cc.llr_scale);
+        }
+        return;
+    }
+    // modes 2 / 3: a second Gaussian and the hit decision from two more Philox blocks of the same
+    // (frame, stream): word index with bit 31 / bit 30 set (n < 2^30 variables)
+    const Philox4 p2 = philox4x32_10(q | 0x80000000u, (uint32_t)frame, (uint32_t)(frame >> 32), cc.stream_id, cc.k0, cc.k1);
+    const Philox4 pu = philox4x32_10(q | 0x40000000u, (uint32_t)frame, (uint32_t)(frame >> 32), cc.stream_id, cc.k0, cc.k1);
+    float g2[4];
+    box_muller(p2.x, p2.y, g2[0], g2[1]);
+    box_muller(p2.z, p2.w, g2[2], g2[3]);
+    const uint32_t u[4] = {pu.x, pu.y, pu.z, pu.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float sym = ((bits4 >> i) & 1u) ? cc.amp : -cc.amp;
-        const float y = __fmaf_rn(cc.noise_dev, g[i], sym);
-        out[i] = __fmul_rn(y, cc.llr_scale);
+        const bool hit = cc.hit_threshold == 0xffffffffu || u[i] < cc.hit_threshold;
+        float y = __fmaf_rn(cc.noise_dev, g[i], sym);
+        if (hit) y = __fmaf_rn(cc.a2, g2[i], y);
+        out[i] = __fmul_rn(y, hit ? cc.l_hit : cc.llr_scale);
     }
 }
 

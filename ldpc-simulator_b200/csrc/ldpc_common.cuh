@@ -112,10 +112,10 @@ int qc_jit_decode(const ldpc_graph* g, int64_t frames, int max_iter, unsigned fl
 int qc_resident_kind(const ldpc_graph* g, unsigned flags);
 
 // ---- channel / counters, mc.cu ---------------------------------------------
-int channel_fill(int n, int dtype, int64_t frames, double speed, double snr_db, int quirk, uint64_t seed,
+int channel_fill(int n, int dtype, int64_t frames, const ldpc_channel& ch, uint64_t seed,
                  uint32_t stream_id, uint64_t frame_offset, const uint8_t* codeword_dev, int64_t codeword_stride,
                  void* llr_dev, cudaStream_t stream);
-void channel_params(double speed, double snr_db, int quirk, uint64_t seed, uint32_t stream_id, McParams* mc);
+int channel_params(const ldpc_channel& ch, int n, uint64_t seed, uint32_t stream_id, McParams* mc);
 int count_errors(int n, int k_info, int64_t frames, const uint8_t* z_dev, const uint8_t* ok_dev,
                  const int32_t* conv_dev, const uint8_t* codeword_dev, int64_t codeword_stride,
                  const uint8_t* info_mask_dev, const float* norm_dev, int k_norm,

@@ -90,31 +90,58 @@ k_count_errors(int n, int k_info, int64_t frames, const uint8_t* __restrict__ z,
 
 }  // namespace
 
-// channel_flags: LDPC_CHANNEL_SIGMA_SQ (the reference's noise deviation), LDPC_CHANNEL_AMP_07 (modulation 2)
-static ChannelConst make_channel_const(double speed, double snr_db, int channel_flags, uint64_t seed, uint32_t stream_id)
+// Channel.create_channel (channel.py:102-125) -> the constants the device generator needs.
+//   mode 1: y = sym + N(0, sigma^2 or sigma^4) ; LLR = 2 y / sigma^2                      (:56-81)
+//   mode 2: every bit is hit with probability P(a/n < p), a uniform in 0..n-1 (:86-88):
+//           hit:  (sym + s2 g2 + s1 g1) L_c2 ;  else (sym + s1 g1) L_c1                     (:89-96)
+//   mode 3: ((sym + s1 g1 + s2 g2) p + (sym + s1 g1)(1 - p)) L_c3 = (sym + s1 g1 + p s2 g2) L_c3   (:98-100)
+// with s1, s2, L_c1..3 of :104-121 (modes 2/3 use sigma itself as the deviation, no sigma^2 quirk).
+static int make_channel_const(const ldpc_channel& ch, int n, uint64_t seed, uint32_t stream_id, ChannelConst* out)
 {
-    const bool quirk = (channel_flags & LDPC_CHANNEL_SIGMA_SQ) != 0;
-    const double sigma = 1.0 / std::sqrt(2.0 * speed * std::pow(10.0, snr_db * 0.1));   // channel.py:113
+    if (!(ch.speed > 0.0)) { set_error("speed must be positive"); return LDPC_ERR_INVALID; }
+    if (ch.mode < 1 || ch.mode > 3) { set_error("channel mode %d (1, 2 or 3)", ch.mode); return LDPC_ERR_INVALID; }
+    if (ch.mode != 1 && !(ch.p > 0.0 && ch.p <= 1.0)) { set_error("interference share p must be in (0, 1]"); return LDPC_ERR_INVALID; }
+    const double lin1 = std::pow(10.0, ch.snr_db * 0.1), lin2 = std::pow(10.0, ch.interference_snr_db * 0.1);
+    const double sigma = 1.0 / std::sqrt(2.0 * ch.speed * lin1);                          // channel.py:113
     ChannelConst cc;
-    cc.noise_dev = (float)(quirk ? sigma * sigma : sigma);                              // channel.py:68
-    cc.llr_scale = (float)(2.0 / (sigma * sigma));                                      // channel.py:80
-    cc.amp = (channel_flags & LDPC_CHANNEL_AMP_07) ? 0.7f : 1.0f;                       // channel.py:49,51
+    cc.amp = ch.modulation == 2 ? 0.7f : 1.0f;                                            // channel.py:49,51
+    cc.a2 = 0.f; cc.l_hit = 0.f; cc.hit_threshold = 0u;
+    if (ch.mode == 1) {
+        cc.noise_dev = (float)(ch.sigma_sq_quirk ? sigma * sigma : sigma);                // channel.py:68
+        cc.llr_scale = (float)(2.0 / (sigma * sigma));                                    // channel.py:80
+    } else if (ch.mode == 2) {
+        cc.noise_dev = (float)sigma;
+        cc.llr_scale = (float)(4.0 * ch.speed * lin1);                                                     // L_c1
+        cc.a2 = (float)(1.0 / std::sqrt(2.0 * ch.speed * lin2 * ch.p));                                    // sigma2
+        cc.l_hit = (float)(4.0 * ch.speed / (1.0 / lin1 + 1.0 / (lin2 * ch.p)));                           // L_c2
+        const double hit = std::min(1.0, std::ceil(ch.p * n - 1e-12) / (double)n);                         // P(a/n < p)
+        cc.hit_threshold = hit >= 1.0 ? 0xffffffffu : (uint32_t)std::max(1.0, hit * 4294967296.0);
+    } else {
+        cc.noise_dev = (float)sigma;
+        cc.llr_scale = 0.f;
+        cc.a2 = (float)(ch.p / std::sqrt(2.0 * ch.speed * lin2));                                          // p * sigma2
+        cc.l_hit = (float)(4.0 * ch.p * ch.speed / (2.0 / lin2) + 4.0 * ch.speed * (1.0 - ch.p) * lin1);   // L_c3
+        cc.hit_threshold = 0xffffffffu;
+    }
     cc.k0 = (uint32_t)seed;
     cc.k1 = (uint32_t)(seed >> 32);
     cc.stream_id = stream_id;
-    return cc;
+    *out = cc;
+    return LDPC_OK;
 }
 
-int channel_fill(int n, int dtype, int64_t frames, double speed, double snr_db, int quirk, uint64_t seed,
+int channel_fill(int n, int dtype, int64_t frames, const ldpc_channel& ch, uint64_t seed,
                  uint32_t stream_id, uint64_t frame_offset, const uint8_t* codeword_dev, int64_t codeword_stride,
                  void* llr_dev, cudaStream_t stream)
 {
-    if (n <= 0 || frames < 0 || !llr_dev || !(speed > 0.0)) { set_error("bad channel arguments"); return LDPC_ERR_INVALID; }
+    if (n <= 0 || frames < 0 || !llr_dev) { set_error("bad channel arguments"); return LDPC_ERR_INVALID; }
+    ChannelConst cc;
+    int rc = make_channel_const(ch, n, seed, stream_id, &cc);
+    if (rc) return rc;
     if (frames == 0) return LDPC_OK;
     DeviceInfo di;
-    int rc = get_device_info(&di);
+    rc = get_device_info(&di);
     if (rc) return rc;
-    const ChannelConst cc = make_channel_const(speed, snr_db, quirk, seed, stream_id);
     const int64_t items = frames * ((n + 3) / 4);
     const int grid = (int)std::min<int64_t>((items + 255) / 256, (int64_t)di.sm_count * 16);
     if (dtype == LDPC_F64)
@@ -125,14 +152,20 @@ int channel_fill(int n, int dtype, int64_t frames, double speed, double snr_db, 
     return LDPC_OK;
 }
 
-void channel_params(double speed, double snr_db, int quirk, uint64_t seed, uint32_t stream_id, McParams* mc)
+int channel_params(const ldpc_channel& ch, int n, uint64_t seed, uint32_t stream_id, McParams* mc)
 {
-    const ChannelConst cc = make_channel_const(speed, snr_db, quirk, seed, stream_id);
+    ChannelConst cc;
+    const int rc = make_channel_const(ch, n, seed, stream_id, &cc);
+    if (rc) return rc;
     mc->noise_dev = cc.noise_dev;
     mc->llr_scale = cc.llr_scale;
     mc->amp = cc.amp;
+    mc->a2 = cc.a2;
+    mc->l_hit = cc.l_hit;
+    mc->hit_threshold = cc.hit_threshold;
     mc->seed = seed;
     mc->stream_id = stream_id;
+    return LDPC_OK;
 }
 
 int count_errors(int n, int k_info, int64_t frames, const uint8_t* z_dev, const uint8_t* ok_dev,

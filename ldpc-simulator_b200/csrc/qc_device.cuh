@@ -23,6 +23,9 @@ struct McParams {               // in-kernel channel (awgn_philox.cuh); enabled 
     float noise_dev = 1.f;      // sigma^2 (reference quirk, channel.py:68) or sigma
     float llr_scale = 2.f;      // 2 / sigma^2 (channel.py:80)
     float amp = 1.f;            // symbol amplitude (channel.py:49,51)
+    float a2 = 0.f;             // channel modes 2 / 3 (channel.py:83-100), see ChannelConst
+    float l_hit = 0.f;
+    uint32_t hit_threshold = 0;
     uint64_t seed = 0;
     uint32_t stream_id = 0;
     uint64_t frame_offset = 0;

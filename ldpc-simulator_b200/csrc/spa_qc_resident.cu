@@ -100,6 +100,7 @@ k_qc_resident(const __grid_constant__ QcParams<MB, DC> p, const float* __restric
 
     ChannelConst cc;
     cc.noise_dev = mc.noise_dev; cc.llr_scale = mc.llr_scale; cc.amp = mc.amp;
+    cc.a2 = mc.a2; cc.l_hit = mc.l_hit; cc.hit_threshold = mc.hit_threshold;
     cc.k0 = (uint32_t)mc.seed; cc.k1 = (uint32_t)(mc.seed >> 32); cc.stream_id = mc.stream_id;
 
     for (long long f = blockIdx.x;; ) {

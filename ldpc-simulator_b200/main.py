@@ -9,8 +9,9 @@ frame is generated, decoded and counted on the GPU (mc_driver.MonteCarloEngine).
 ``args.threads`` is accepted and recorded; parallelism comes from the GPU batch and, when
 ``torch.distributed`` is initialised, from sharding frames over ranks.
 
-Only the pipeline the north-star names is supported: mode 1 (AWGN), modulation 1 (BPSK, or the
-reference's "modulation 2" = symbols of amplitude 0.7), standard encoding; other modes / encoders raise ``NotImplementedError``.  Interleaver settings are
+Supported: channel modes 1 (AWGN, the north-star path), 2 and 3 (interference, channel.py:83-100; Philox
+instead of the reference's Park-Miller stream), modulation 1 (BPSK) and the reference's "modulation 2"
+(symbols of amplitude 0.7), standard encoding; other modes / encoders raise ``NotImplementedError``.  Interleaver settings are
 recorded but are a statistical no-op on this memoryless channel.  ``--adaptive`` runs the sweep
 under ``adaptive.AdaptiveController`` (main.py:620-639 of the reference).
 """
@@ -50,9 +51,8 @@ def snr_grid(initial_snr, end_snr, step_snr):
 
 
 def _check_scope(settings, args, encoding_method):
-    if getattr(args, "mode", 1) != 1:
-        raise NotImplementedError("the GPU channel generator covers mode 1 (AWGN); modes 2 and 3 exist on the host "
-                                  "(Channel.process) only")
+    if getattr(args, "mode", 1) not in (1, 2, 3):
+        raise ValueError("channel mode must be 1, 2 or 3")
     if encoding_method != EncodingMethod.STANDARD:
         raise NotImplementedError("only the standard (generator matrix) encoder is supported")
     # An interleaver setting is accepted and reported but moves no data: the channel is memoryless and
@@ -76,7 +76,8 @@ def run_simulation(encoder_decoder_data, settings, args, encoding_method, ru_dat
         sigma_sq_quirk=not getattr(args, "no_sigma_sq_quirk", False),
         seed=getattr(args, "seed", None) if getattr(args, "seed", None) is not None else int(time.time() * 1e6) % (2 ** 63),
         normalized_llr=bool(getattr(args, "normalized_llr", False)),
-        modulation=getattr(args, "modulation", 1),
+        modulation=getattr(args, "modulation", 1), mode=getattr(args, "mode", 1), p=getattr(args, "p", 0.1),
+        interference_snr=getattr(args, "interference_snr", 0.0) if getattr(args, "mode", 1) != 1 else 0.0,   # main.py:215
     )
     say("Processing blocks over the SNR grid...")
     say("-" * 60)

@@ -70,7 +70,7 @@ def split_frames(total, rank, world):
 class MonteCarloEngine:
     def __init__(self, edd, *, graph="std", precision="f64", max_iterations=20, early_termination=True,
                  fix_odd_check_sign=False, sigma_sq_quirk=True, seed=0x5EED, device=None, group=None,
-                 kernel_flags=0, normalized_llr=False, modulation=1):
+                 kernel_flags=0, normalized_llr=False, modulation=1, mode=1, p=0.1, interference_snr=0.0):
         import torch
         self.torch = torch
         self.edd = edd
@@ -83,8 +83,9 @@ class MonteCarloEngine:
         if normalized_llr:
             # the metric (spa_decoder.py:210-228) is carried by the generic kernels only
             self.flags |= _native.FLAG_NORM_LLR | _native.FLAG_FORCE_GENERIC
-        # channel flags of ldpc_mc_run: the reference's noise deviation, +-0.7 symbols for modulation 2
-        self.quirk = int(bool(sigma_sq_quirk)) | (_native.CHANNEL_AMP_07 if int(modulation) == 2 else 0)
+        # the channel of Channel.create_channel(speed, snr, interference_snr, mode, p, modulation) (channel.py:102-125)
+        self.quirk = int(bool(sigma_sq_quirk))
+        self.modulation, self.mode, self.p, self.interference_snr = int(modulation), int(mode), float(p), float(interference_snr)
         self.seed = int(seed)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.group = group
@@ -127,9 +128,12 @@ class MonteCarloEngine:
         if frames_local <= 0:
             return
         ws = self._workspace(frames_local)
-        _native.check(_native.lib().ldpc_mc_run(
+        import ctypes as C
+        desc = _native.ChannelDesc(self.mode, self.modulation, self.quirk, float(speed), float(snr_db),
+                                   self.interference_snr, self.p)
+        _native.check(_native.lib().ldpc_mc_run_ex(
             self.graph.handle, self.dtype, int(frames_local), self.max_iterations, self.flags,
-            float(speed), float(snr_db), self.quirk, self.seed, int(self.rank), int(frame_offset),
+            C.byref(desc), self.seed, int(self.rank), int(frame_offset),
             codeword.data_ptr() if codeword is not None else None,
             (self.n if codeword is not None and codeword.dim() == 2 else 0), self._mask.data_ptr(), self.k,
             counters.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream(self.device).cuda_stream))
