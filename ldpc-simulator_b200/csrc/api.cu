@@ -426,7 +426,7 @@ extern "C" size_t ldpc_mc_workspace_bytes(const ldpc_graph* g, int64_t frames, i
     if (!g || frames < 0) return 0;
     if (dtype == LDPC_F32_FAST && qc_resident_kind(g, 0) != LDPC_KERNEL_GENERIC) return 256;
     const size_t esz = dtype == LDPC_F64 ? 8 : 4;
-    const int64_t F = std::max<int64_t>(frames, 1);
+    const int64_t F = (std::max<int64_t>(frames, 1) + 31) / 32 * 32;      // ldpc_mc_run works in chunks of 32 frames
     return align_up((size_t)F * g->n * esz, 256) + align_up((size_t)F * g->n, 256) + align_up((size_t)F * 4, 256) * 2 +
            align_up((size_t)F, 256) + generic_workspace_bytes(g, F, dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32);
 }
