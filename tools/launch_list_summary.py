@@ -1,3 +1,5 @@
+"""Share of each kernel in an ncu launch list:  python tools/launch_list_summary.py launches.csv
+(the CSV of `ncu --metrics gpu__time_duration.sum --csv --log-file launches.csv <command>`)."""
 import csv,sys
 from collections import defaultdict
 rows=[r for r in csv.reader(open(sys.argv[1])) if len(r)>14 and r[0].isdigit()]
