@@ -78,7 +78,7 @@ class MonteCarloEngine:
         self.precision = precision
         self.dtype = _PRECISIONS[precision]
         self.max_iterations = int(max_iterations)
-        self.flags = (_native.FLAG_EARLY_TERM if early_termination else 0) | \
+        self.flags = ((_native.FLAG_EARLY_TERM | _native.FLAG_COMPACT) if early_termination else 0) | \
                      (_native.FLAG_FIX_ODD_SIGN if fix_odd_check_sign else 0) | int(kernel_flags)
         if normalized_llr:
             # the metric (spa_decoder.py:210-228) is carried by the generic kernels only

@@ -107,11 +107,11 @@ class SPA_Decoder:
             raise ValueError(f"unknown precision {name!r}")
         return name, _PRECISIONS[name]
 
-    def _flags(self, early_termination=None, compact=False, table_kernel=False, jit=True, replay=True):
+    def _flags(self, early_termination=None, compact=None, table_kernel=False, jit=True, replay=True):
         s = self.m_pSettings
         early = getattr(s, "is_early_termination", lambda: True)() if early_termination is None else early_termination
         flags = _native.FLAG_EARLY_TERM if early else 0
-        if compact:
+        if compact or (compact is None and early):     # same results; never slower than masking
             flags |= _native.FLAG_COMPACT
         if table_kernel:
             flags |= _native.FLAG_TABLE_KERNEL
@@ -124,7 +124,7 @@ class SPA_Decoder:
         return flags
 
     # ---- batched decode, host buffers (the end-to-end call) -------------------------
-    def decode_batch(self, llr, *, precision=None, early_termination=None, compact=False, want_z=True,
+    def decode_batch(self, llr, *, precision=None, early_termination=None, compact=None, want_z=True,
                      want_bits=False, want_posterior=False, normalized_llr=None, max_iterations=None,
                      table_kernel=False, jit=True, replay=True):
         """Decode F frames given as a host array ``llr`` [F, n] (numpy, or a pinned CPU torch tensor).
@@ -178,7 +178,7 @@ class SPA_Decoder:
         return BatchResult(z, zbits, ok, conv, post, norm)
 
     # ---- batched decode, device tensors (async on the current stream) ---------------
-    def decode_batch_device(self, llr, *, precision=None, early_termination=None, compact=False,
+    def decode_batch_device(self, llr, *, precision=None, early_termination=None, compact=None,
                             want_posterior=False, normalized_llr=False, max_iterations=None, workspace=None,
                             table_kernel=False, jit=True, force_generic=False):
         """``llr``: CUDA tensor [F, n] (float64 for 'f64', float32 otherwise).  Returns CUDA tensors."""
