@@ -36,6 +36,10 @@ def main():
     ap.add_argument("--fix-odd-check-sign", action="store_true")
     ap.add_argument("--no-sigma-sq-quirk", action="store_true")
     ap.add_argument("--seed", type=int, default=0x5EED)
+    ap.add_argument("--mode", type=int, choices=[1, 2, 3], default=1, help="channel mode of channel.py (2, 3: interference)")
+    ap.add_argument("--p", type=float, default=0.1)
+    ap.add_argument("--interference-snr", type=float, default=0.0)
+    ap.add_argument("--modulation", type=int, choices=[1, 2], default=1)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
 
@@ -66,7 +70,8 @@ def main():
         edd = EncoderDecoderData(h=SparseMatrix(sparse_matrix=h))
         label = a.code
     eng = MonteCarloEngine(edd, graph=a.graph, precision=a.precision, max_iterations=a.iterations,
-                           fix_odd_check_sign=a.fix_odd_check_sign, sigma_sq_quirk=not a.no_sigma_sq_quirk, seed=a.seed)
+                           fix_odd_check_sign=a.fix_odd_check_sign, sigma_sq_quirk=not a.no_sigma_sq_quirk, seed=a.seed,
+                           mode=a.mode, p=a.p, interference_snr=a.interference_snr, modulation=a.modulation)
     t0 = time.time()
     points, raw = [], []
     for snr in snr_grid(*a.snr):
