@@ -291,6 +291,12 @@ def main():
     st.set_max_iterations(MAX_ITER)
     st.set_precision("f32_fast")
     st.set_early_termination(False)
+    if os.environ.get("LDPC_BENCH_ONE_FRAME"):      # A/B: the one-frame-per-thread resident kernel
+        st.set_one_frame_kernel(True)
+    if os.environ.get("LDPC_BENCH_PAIR_SCATTER"):   # A/B: pair kernel, in-place posterior accumulation, messages in TMEM
+        st.set_pair_scatter_kernel(True)
+    if os.environ.get("LDPC_BENCH_PAIR_REGS"):      # A/B: pair kernel with the messages in registers instead of TMEM
+        st.set_pair_regs_kernel(True)
     dec = SPA_Decoder(Edd(), st)
     g = dec.graph
     assert g.is_qc and g.qc_z == 96, "quasi-cyclic fast path not detected"

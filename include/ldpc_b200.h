@@ -72,6 +72,13 @@ typedef enum ldpc_dtype {
 
 #define LDPC_FLAG_NO_REPLAY     0x80u /* ldpc_decode_batch_host: do not replay tiny calls (<= 32 frames, generic kernels)
                                          from a captured CUDA graph; launch the kernels one by one (tests) */
+#define LDPC_FLAG_ONE_FRAME     0x100u /* resident path: use the one-frame-per-thread kernel even for batches that would
+                                          run the two-frames-per-thread kernel (identical results; tests, A/B timing) */
+#define LDPC_FLAG_PAIR_REGS     0x200u /* resident path, two-frames-per-thread kernel: keep the messages in registers
+                                          instead of tensor memory (identical results; tests, A/B timing) */
+#define LDPC_FLAG_PAIR_SCATTER  0x400u /* resident path, two-frames-per-thread kernel: accumulate the posterior in place
+                                          (one barrier per group of block rows) instead of the barrier-free check-node
+                                          phase + gather (identical results; tests, A/B timing) */
 #define LDPC_FLAG_NORM_LLR      0x40u /* ldpc_mc_run: also accumulate the "normalized LLR" metric (spa_decoder.py:210-228)
                                          in counters[5]; runs the generic kernels, which carry the metric */
 

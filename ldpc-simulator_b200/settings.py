@@ -25,6 +25,9 @@ class Settings:
         self._precision = "f64"            # "f64" parity kernel | "f32" | "f32_fast" resident QC kernel
         self._early_termination = True     # reference behaviour (spa_decoder.py:231-241)
         self._fix_odd_check_sign = False   # reference behaviour: do NOT compensate
+        self._one_frame_kernel = False     # resident path: force the one-frame-per-thread kernel (same results)
+        self._pair_regs_kernel = False     # resident path: pair kernel with the messages in registers, not TMEM
+        self._pair_scatter_kernel = False  # resident path: pair kernel with in-place posterior accumulation (TMEM messages)
 
     # -- reference surface ----------------------------------------------------
     def set_blocks_cnt(self, i_num_blocks): self._i_blocks_cnt = i_num_blocks
@@ -66,3 +69,9 @@ class Settings:
     def is_early_termination(self): return self._early_termination
     def set_fix_odd_check_sign(self, flag): self._fix_odd_check_sign = bool(flag)
     def is_fix_odd_check_sign(self): return self._fix_odd_check_sign
+    def set_one_frame_kernel(self, flag): self._one_frame_kernel = bool(flag)
+    def is_one_frame_kernel(self): return self._one_frame_kernel
+    def set_pair_regs_kernel(self, flag): self._pair_regs_kernel = bool(flag)
+    def is_pair_regs_kernel(self): return self._pair_regs_kernel
+    def set_pair_scatter_kernel(self, flag): self._pair_scatter_kernel = bool(flag)
+    def is_pair_scatter_kernel(self): return self._pair_scatter_kernel

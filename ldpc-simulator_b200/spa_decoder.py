@@ -121,6 +121,12 @@ class SPA_Decoder:
             flags |= _native.FLAG_NO_REPLAY
         if getattr(s, "is_fix_odd_check_sign", lambda: False)():
             flags |= _native.FLAG_FIX_ODD_SIGN
+        if getattr(s, "is_one_frame_kernel", lambda: False)():
+            flags |= _native.FLAG_ONE_FRAME
+        if getattr(s, "is_pair_regs_kernel", lambda: False)():
+            flags |= _native.FLAG_PAIR_REGS
+        if getattr(s, "is_pair_scatter_kernel", lambda: False)():
+            flags |= _native.FLAG_PAIR_SCATTER
         return flags
 
     # ---- batched decode, host buffers (the end-to-end call) -------------------------

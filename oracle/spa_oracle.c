@@ -87,6 +87,8 @@ static inline double clip_unit(double r)
  *   norm_out    the value left in _d_summarize_normalized_llr (:237-239,
  *               249-251) when calc_norm, may be NULL
  *   scratch     2*nnz + 3*n doubles
+ *   odd_fix     0 = the reference.  1 = test-only variant matching the product's
+ *               non-default LDPC_FLAG_FIX_ODD_SIGN switch (see the check-node pass)
  * returns 1 when the frame converged (Result.OK, :241), 0 otherwise (:253).
  *
  * max_iter must be >= 1: with max_iter <= 0 the reference loops until the
@@ -96,7 +98,7 @@ static int decode_one(int m, int n, const int32_t *rp, const int32_t *ci,
                       const int32_t *cp, const int32_t *cedge,
                       const double *llr, int max_iter, int calc_norm, int k_norm,
                       uint8_t *z_out, int32_t *conv_it, double *post_out,
-                      double *post_trace, double *norm_out, double *scratch)
+                      double *post_trace, double *norm_out, double *scratch, int odd_fix)
 {
     const int64_t nnz = rp[m];
     double *M = scratch;            /* variable->check messages, CSR edge order */
@@ -134,6 +136,9 @@ static int decode_one(int m, int n, const int32_t *rp, const int32_t *ci,
                         if (u != q) r *= tbuf[u];
                 }
                 E[a + q] = 2.0 * atanh(clip_unit(r));         /* :167-168 */
+                /* NOT the reference (odd_fix = 0 everywhere the reference is restated): the product's
+                 * non-default fix_odd_check_sign switch negates the extrinsics of odd-degree checks. */
+                if (odd_fix && (d & 1)) E[a + q] = -E[a + q];
             }
         }
         /* ---- posterior, hard decision, spa_decoder.py:173-188 ---- */
@@ -187,6 +192,8 @@ static size_t scratch_doubles(int64_t nnz, int n) { return (size_t)(2 * nnz + 3 
  * Returns 0, or -1 on bad arguments / allocation failure.
  */
 typedef struct {
+    int odd_fix;
+    double *trace;          /* [F][max_iter][n] posteriors of every executed pass, or NULL */
     int m, n, max_iter, calc_norm, k_norm;
     const int32_t *rp, *ci, *cp, *cedge;
     int64_t F, nnz;
@@ -212,7 +219,9 @@ static void *batch_worker(void *arg)
         int good = decode_one(job->m, n, job->rp, job->ci, job->cp, job->cedge,
                               job->llr + (size_t)f * n, job->max_iter, job->calc_norm, job->k_norm,
                               job->z + (size_t)f * n, &cit,
-                              job->post ? job->post + (size_t)f * n : NULL, NULL, &nl, scratch);
+                              job->post ? job->post + (size_t)f * n : NULL,
+                              job->trace ? job->trace + (size_t)f * job->max_iter * n : NULL, &nl, scratch,
+                              job->odd_fix);
         job->conv_it[f] = cit;
         job->ok[f] = (uint8_t)good;
         if (job->norm) job->norm[f] = nl;
@@ -221,11 +230,32 @@ static void *batch_worker(void *arg)
     return NULL;
 }
 
+int spa_oracle_decode_batch_ex(int m, int n, const int32_t *rp, const int32_t *ci,
+                               int64_t F, const double *llr, int max_iter,
+                               int calc_norm, int k_norm,
+                               uint8_t *z, int32_t *conv_it, uint8_t *ok,
+                               double *post, double *norm, int nthreads,
+                               int odd_fix, double *post_trace);
+
 int spa_oracle_decode_batch(int m, int n, const int32_t *rp, const int32_t *ci,
                             int64_t F, const double *llr, int max_iter,
                             int calc_norm, int k_norm,
                             uint8_t *z, int32_t *conv_it, uint8_t *ok,
                             double *post, double *norm, int nthreads)
+{
+    return spa_oracle_decode_batch_ex(m, n, rp, ci, F, llr, max_iter, calc_norm, k_norm, z, conv_it, ok,
+                                      post, norm, nthreads, 0, NULL);
+}
+
+/* Same, plus odd_fix (see decode_one; 0 = the reference) and post_trace [F][max_iter][n] (or NULL):
+ * the posterior of every executed pass of every frame (rows of passes that were not executed are
+ * left untouched). */
+int spa_oracle_decode_batch_ex(int m, int n, const int32_t *rp, const int32_t *ci,
+                               int64_t F, const double *llr, int max_iter,
+                               int calc_norm, int k_norm,
+                               uint8_t *z, int32_t *conv_it, uint8_t *ok,
+                               double *post, double *norm, int nthreads,
+                               int odd_fix, double *post_trace)
 {
     if (m < 0 || n <= 0 || F < 0 || max_iter < 1 || !rp || !ci || !llr || !z || !conv_it || !ok)
         return -1;
@@ -239,7 +269,7 @@ int spa_oracle_decode_batch(int m, int n, const int32_t *rp, const int32_t *ci,
         nthreads = online > 0 ? (int)online : 1;
     }
     if ((int64_t)nthreads > F) nthreads = F > 0 ? (int)F : 1;
-    batch_job job = { m, n, max_iter, calc_norm, k_norm, rp, ci, cp, cedge, F, nnz, llr,
+    batch_job job = { odd_fix, post_trace, m, n, max_iter, calc_norm, k_norm, rp, ci, cp, cedge, F, nnz, llr,
                       z, ok, conv_it, post, norm, 0, 0 };
     if (nthreads == 1) {
         batch_worker(&job);
@@ -273,7 +303,7 @@ int spa_oracle_decode_trace(int m, int n, const int32_t *rp, const int32_t *ci,
     if (!cp || !cedge || !scratch) { free(cp); free(cedge); free(scratch); return -1; }
     build_column_view(m, n, rp, ci, cp, cedge);
     int good = decode_one(m, n, rp, ci, cp, cedge, llr, max_iter, 0, 0, z, conv_it, NULL,
-                          post_trace, NULL, scratch);
+                          post_trace, NULL, scratch, 0);
     free(cp); free(cedge); free(scratch);
     return good;
 }

@@ -39,6 +39,10 @@ def _load():
     lib.spa_oracle_decode_batch.restype = C.c_int
     lib.spa_oracle_decode_batch.argtypes = [C.c_int, C.c_int, i32p, i32p, C.c_int64, f64p, C.c_int,
                                             C.c_int, C.c_int, u8p, i32p, u8p, f64p, f64p, C.c_int]
+    lib.spa_oracle_decode_batch_ex.restype = C.c_int
+    lib.spa_oracle_decode_batch_ex.argtypes = [C.c_int, C.c_int, i32p, i32p, C.c_int64, f64p, C.c_int,
+                                               C.c_int, C.c_int, u8p, i32p, u8p, f64p, f64p, C.c_int,
+                                               C.c_int, f64p]
     lib.spa_oracle_decode_trace.restype = C.c_int
     lib.spa_oracle_decode_trace.argtypes = [C.c_int, C.c_int, i32p, i32p, f64p, C.c_int, u8p, i32p, f64p]
     lib.spa_oracle_sigma.restype = C.c_double
@@ -66,11 +70,13 @@ def _csr(row_ptr, col_idx):
 
 
 def decode_batch(row_ptr, col_idx, n, llr, max_iter, *, want_post=True, calc_norm=False,
-                 k_norm=None, nthreads=0):
+                 k_norm=None, nthreads=0, fix_odd_check_sign=False, want_trace=False):
     """SPA_Decoder.decode (spa_decoder.py:63-280) over a batch of frames.
 
     ``llr`` is [F, n] (or [n]); returns dict(z, conv_it, ok, post, norm) where
     ``z`` is the reference's complemented hard decision (_decoded_data).
+    ``fix_odd_check_sign`` (NOT the reference; default off) mirrors the product's non-default switch of
+    the same name; ``want_trace`` adds ``post_trace`` [F, max_iter, n] (NaN where a pass did not run).
     """
     lib = _load()
     rp, ci = _csr(row_ptr, col_idx)
@@ -85,13 +91,18 @@ def decode_batch(row_ptr, col_idx, n, llr, max_iter, *, want_post=True, calc_nor
     norm = np.zeros(F, dtype=np.float64) if calc_norm else None
     if k_norm is None:
         k_norm = n - m
-    rc = lib.spa_oracle_decode_batch(m, n, _p(rp, C.c_int32), _p(ci, C.c_int32), F,
-                                     _p(llr, C.c_double), int(max_iter), int(calc_norm), int(k_norm),
-                                     _p(z, C.c_uint8), _p(conv, C.c_int32), _p(ok, C.c_uint8),
-                                     _p(post, C.c_double), _p(norm, C.c_double), int(nthreads))
+    trace = np.full((F, int(max_iter), n), np.nan) if want_trace else None
+    rc = lib.spa_oracle_decode_batch_ex(m, n, _p(rp, C.c_int32), _p(ci, C.c_int32), F,
+                                        _p(llr, C.c_double), int(max_iter), int(calc_norm), int(k_norm),
+                                        _p(z, C.c_uint8), _p(conv, C.c_int32), _p(ok, C.c_uint8),
+                                        _p(post, C.c_double), _p(norm, C.c_double), int(nthreads),
+                                        int(bool(fix_odd_check_sign)), _p(trace, C.c_double))
     if rc != 0:
         raise ValueError("spa_oracle_decode_batch rejected its arguments")
-    return dict(z=z, conv_it=conv, ok=ok, post=post, norm=norm)
+    out = dict(z=z, conv_it=conv, ok=ok, post=post, norm=norm)
+    if want_trace:
+        out["post_trace"] = trace
+    return out
 
 
 def decode_trace(row_ptr, col_idx, n, llr, max_iter):

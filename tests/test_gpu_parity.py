@@ -544,3 +544,51 @@ def test_frame_order_and_batch_split_invariance():
     assert np.array_equal(shuf.z, full.z[perm]) and np.array_equal(shuf.post, full.post[perm])
     halves = [dec.decode_batch(llr[:300], want_posterior=True), dec.decode_batch(llr[300:], want_posterior=True)]
     assert np.array_equal(np.concatenate([h.post for h in halves]), full.post)
+
+
+# ---- two-frames-per-thread resident kernel (csrc/qc_kernel_pair.cuh) --------------------------------
+@pytest.mark.parametrize("variant", ["gather", "scatter_tmem", "scatter_regs"])
+@pytest.mark.parametrize("name,frames,early,fix", [
+    ("wimax_2304_0.5", 4096, False, False), ("wimax_2304_0.5", 4097, True, True), ("wimax_2304_0.5", 1999, True, False),
+    ("wimax_576_0.5", 3001, True, True), ("wimax_576_0.5", 2048, False, False),
+])
+def test_pair_kernel_is_bit_identical_to_the_one_frame_kernel(name, frames, early, fix, variant):
+    """The pair kernel evaluates the same IEEE operations per frame (packed fp32 = two independent lanes):
+    decisions, iteration, syndrome AND posteriors must be identical, for even and odd frame counts, with
+    and without early termination (a frame of a pair that converges first is written out at once)."""
+    code = load_code(name)
+    rng = np.random.default_rng(frames)
+    llr = awgn_llr(rng, frames, code.n, np.resize(np.array([1.0, 1.6, 2.2, 3.0]), frames)).astype(np.float32)
+    # gather (the default): barrier-free check-node phase + gather variable-node phase, messages in tensor memory;
+    # scatter_tmem / scatter_regs: in-place posterior accumulation with the messages in tensor memory / registers
+    kw = {"gather": {}, "scatter_tmem": {"pair_scatter_kernel": True}, "scatter_regs": {"pair_regs_kernel": True}}[variant]
+    pair = make_decoder(code, 20, "f32_fast", fix_odd_check_sign=fix, **kw).decode_batch(
+        llr, want_posterior=True, want_bits=True, early_termination=early)
+    one = make_decoder(code, 20, "f32_fast", fix_odd_check_sign=fix, one_frame_kernel=True).decode_batch(
+        llr, want_posterior=True, want_bits=True, early_termination=early)
+    assert np.array_equal(pair.ok, one.ok)
+    assert np.array_equal(pair.conv_it, one.conv_it)
+    assert np.array_equal(pair.z, one.z)
+    assert np.array_equal(pair.zbits, one.zbits)
+    assert np.array_equal(pair.post, one.post)
+    if fix:
+        assert 0.05 < pair.ok.mean() < 1.0        # a mix of converged and failed frames inside the pairs
+
+
+def test_pair_kernel_monte_carlo_counters_equal_the_one_frame_kernel():
+    """In-kernel Philox channel + error counters: both kernels must count the same events."""
+    import _native
+    import torch
+    from encoder_decoder_data import EncoderDecoderData
+    from mc_driver import MonteCarloEngine
+    edd = EncoderDecoderData(h=load_code("wimax_2304_0.5").sparse_matrix())
+
+    def run(flags):
+        eng = MonteCarloEngine(edd, graph="alist", max_iterations=20, precision="f32_fast", early_termination=True,
+                               fix_odd_check_sign=True, kernel_flags=flags, seed=1234, sigma_sq_quirk=False)
+        counters = torch.zeros(5, dtype=torch.int64, device="cuda")
+        eng.launch(5001, 0.5, 1.6, counters, frame_offset=3)
+        return counters.cpu().tolist()
+    a, b, c, d = run(0), run(_native.FLAG_ONE_FRAME), run(_native.FLAG_PAIR_REGS), run(_native.FLAG_PAIR_SCATTER)
+    assert a == b == c == d
+    assert a[0] == 5001 and 0 < a[1] < 5001
