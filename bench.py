@@ -150,10 +150,13 @@ def run_reference_arm(args):
     value = bits / t_total / 1e9
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": args.gpus,
+        "cores": cores, "frames_per_step": per_step,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"WiMAX 802.16e n=2304 r1/2 raw ALIST H, SPA {MAX_ITER} fixed iterations, "
-                               f"{per_step} frames per step (bounded sample), Eb/N0 {EBN0_DB} dB, all-zero codeword"},
+                               f"{per_step} frames per step (bounded sample of the GPU arm's batch: a rate metric, same code, "
+                               f"iterations and channel), Eb/N0 {EBN0_DB} dB, all-zero codeword; {cores} host threads -- the "
+                               f"ratio to the GPU arm scales with the host's core count"},
         "cpu_baseline": {"value": value, "unit": "Gbit/s", "cores": cores, "kind": "port",
                          "sample": f"{per_step} frames per step x {args.steps} steps, C port of spa_decoder.py:63-280 "
                                    f"(the reference itself is pure Python and cannot travel to the GPU box), "
@@ -376,20 +379,98 @@ def main():
     ok_frac = float(out.ok.float().mean().item())
 
     # ---- end to end: pinned host LLRs in, packed decisions out ---------------------------------------
-    for _ in range(2):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = world * F * k * args.steps / float(dt.item()) / 1e9
     words = (n + 31) // 32
+
+    def timed_host(step):
+        for _ in range(2):
+            step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = step()
+        torch.cuda.synchronize()
+        mine = time.perf_counter() - t0
+        dt = torch.tensor([mine], dtype=torch.float64, device=dev)
+        every = [torch.zeros_like(dt) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(every, dt)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        else:
+            every = [dt]
+        return float(dt.item()), [float(t.item()) for t in every], res
+
+    t_e2e, t_ranks, res32 = timed_host(step_host)
+    e2e_value = world * F * k * args.steps / t_e2e / 1e9
     h2d = F * n * 4
     d2h = F * (words * 4 + 4 + 1)
+    e2e = {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "h2d_gbs_whole_job": world * h2d * args.steps / t_e2e / 1e9,
+           "per_rank_gbit_s": [F * k * args.steps / t / 1e9 for t in t_ranks],
+           "note": "fp32 LLRs from pinned host memory; bound by the host->device copy (%.2f GB per step and GPU); "
+                   "on the multi-GPU box all ranks share one host's memory / PCIe root complexes" % (h2d / 1e9)}
+
+    # the same call with half precision LLRs on the host (LDPC_FLAG_LLR_F16): a separate, labelled number --
+    # not the reference's input type.  Agreement of the decisions with the fp32-ingest run is measured here.
+    llr_host16 = torch.empty((F, n), dtype=torch.float16).pin_memory()
+    llr_host16.copy_(llr_host)
+
+    def step_host16():
+        return dec.decode_batch(llr_host16, want_z=False, want_bits=True, llr_f16=True)
+
+    t_16, t16_ranks, res16 = timed_host(step_host16)
+    e2e16 = {"value": world * F * k * args.steps / t_16 / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": F * n * 2,
+             "d2h_bytes_per_step": d2h, "h2d_gbs_whole_job": world * F * n * 2 * args.steps / t_16 / 1e9,
+             "per_rank_gbit_s": [F * k * args.steps / t / 1e9 for t in t16_ranks],
+             "decision_bit_agreement_vs_fp32_ingest": float(1.0 - np.unpackbits(res16.zbits ^ res32.zbits).mean() * words * 32 / n),
+             "syndrome_agreement_vs_fp32_ingest": float((res16.ok == res32.ok).mean()),
+             "note": "LLRs rounded to IEEE half on the host, widened to fp32 on the device; this workload (reference sign "
+                     "convention, 2 dB) never converges, so its decisions are those of a chaotic trajectory"}
+    del llr_host16
+
+    # ---- the Monte-Carlo path: in-kernel Philox channel + decode + counters, one all-reduce per interval ----
+    from encoder_decoder_data import EncoderDecoderData
+    from matrix_sparse import SparseMatrix
+    from mc_driver import MonteCarloEngine, run_intervals
+    edd = EncoderDecoderData(h=SparseMatrix(sparse_matrix=h))
+    eng = MonteCarloEngine(edd, graph="alist", precision="f32_fast", max_iterations=MAX_ITER, early_termination=False,
+                           sigma_sq_quirk=False, seed=0x5EED, device=dev)
+    timers = []
+
+    def mc_launch(frames_local, counters, frame_offset):
+        eng.launch(frames_local, SPEED, EBN0_DB, counters, frame_offset=frame_offset)
+
+    def mc_run(intervals, record):
+        total, _ = run_intervals(mc_launch, device=dev, rank=rank, world=world, group=None, distributed=world > 1,
+                                 frames=world * F * intervals, interval_frames=world * F, frame_cursor=0,
+                                 timers=timers if record else None)
+        return total
+
+    mc_run(2, False)
+    barrier()
+    mc_l0 = _native.launches()
+    m_beg, m_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    m_beg.record()
+    mc_total = mc_run(args.steps, True)
+    m_end.record()
+    barrier()
+    mc_wall = time.perf_counter() - t0
+    mc_ms = torch.tensor([m_beg.elapsed_time(m_end)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(mc_ms, op=dist.ReduceOp.MAX)
+    mc_ms = float(mc_ms.item())
+    mc = {"value": world * F * k * args.steps / (mc_ms * 1e-3) / 1e9, "unit": "Gbit/s", "ms_per_interval": mc_ms / args.steps,
+          "intervals": args.steps, "frames_per_interval_per_gpu": F, "gpu_launches": int(_native.launches() - mc_l0),
+          "allreduce_us": float(np.median([t["allreduce_us"] for t in timers])) if timers else None,
+          "host_sync_us": float(np.median([t["host_us"] for t in timers])) if timers else None,
+          "kernel_ms": float(np.median([t["kernel_ms"] for t in timers])) if timers else None,
+          "kernel_ms_max": float(np.max([t["kernel_ms"] for t in timers])) if timers else None,
+          "counters": {"frames": int(mc_total.frames), "frame_errors": int(mc_total.frame_errors), "bit_errors": int(mc_total.bit_errors)},
+          "note": "MonteCarloEngine on the bench code: ldpc_mc_run (Philox AWGN generated in the kernel prologue, %d fixed "
+                  "passes, error counters folded in the epilogue), one NCCL all-reduce of the 6 int64 counters per interval "
+                  "INSIDE the timed region (world %d), then the host reads the reduced counters (stopping rule); "
+                  "allreduce_us = device time between the kernel and the end of the all-reduce, host_sync_us = wall time "
+                  "of an interval beyond its device time (rank 0)" % (MAX_ITER, world)}
 
     if rank != 0:
         if world > 1:
@@ -397,8 +478,8 @@ def main():
         return 0
 
     # ---- roofline of the dominant (only) kernel -------------------------------------------------------
-    peak = torch.zeros(1, dtype=torch.float64)
     import ctypes as C
+    import hashlib
     pk = C.c_double()
     _native.check(_native.lib().ldpc_measure_mufu_peak(C.byref(pk), None))
     mufu_peak = pk.value
@@ -411,22 +492,58 @@ def main():
         with open(peaks_path) as f:
             hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     alg_bytes = F * (n * 4 + n + 4 + 1)                     # LLRs in, z bytes + conv_it + ok out
-    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at 131072 frames
-    # (this command, profiles/r1_ncu_final_kernel_summary.txt), scaled per frame
-    NCU_DRAM_BYTES_PER_FRAME = 11441.0      # profiles/r1_ncu_final_kernel_summary.txt: (1210.7 + 288.9) MB / 131072 frames
+    # HBM traffic of the kernel comes from an ncu capture (dram__bytes_read.sum + dram__bytes_write.sum); it is only
+    # quoted while the kernel sources are the ones that were profiled
+    traffic, traffic_src = None, "no ncu capture on record for the current kernel sources"
+    src_hash = hashlib.sha256()
+    for name in ("qc_kernel.cuh", "qc_kernel_pair.cuh", "qc_kernel_gather.cuh"):
+        with open(os.path.join(PKG, "csrc", name), "rb") as f:
+            src_hash.update(f.read())
+    cap_path = os.path.join(REPO, "profiles", "r2_ncu_traffic.json")
+    if os.path.exists(cap_path):
+        with open(cap_path) as f:
+            cap = json.load(f)
+        if cap.get("kernel_src_sha256") == src_hash.hexdigest():
+            traffic = cap["dram_bytes_per_frame"] * F
+            traffic_src = "ncu capture %s (%s), %.0f B per frame; algorithmic %d B per frame" % (
+                cap.get("file"), cap.get("kernel"), cap["dram_bytes_per_frame"], n * 4 + n + 5)
+        else:
+            traffic_src = "kernel sources changed since the ncu capture %s: not quoted" % cap.get("file")
+    sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    # shared memory, algorithmic bytes per edge, pass and frame: posterior read 4 + message to the edge buffer 4 +
+    # message read by the variable node 4 + posterior write 4 n/E
+    smem_bytes = (12.0 + 4.0 * n / edges) * edges * MAX_ITER * F
+    smem_peak = 128.0 * torch.cuda.get_device_properties(dev).multi_processor_count * sm_hz
     roofline = {
         "bound": "sfu", "achieved": sfu_achieved / 1e9, "peak": mufu_peak / 1e9, "unit": "Gop/s",
-        "frac": sfu_achieved / mufu_peak, "traffic": NCU_DRAM_BYTES_PER_FRAME * F,
-        "traffic_note": "HBM bytes per launch from the ncu capture in profiles/ (11.4 KB per frame; algorithmic 11.5 KB = 9216 B LLR row in + 2304 B decisions out + 4 B iteration)",
-        "note": "resident kernel: messages never leave the SM, HBM is not the bound; achieved = 2 algorithmic "
-                "transcendentals per edge and pass / kernel time (CUDA events); peak = MUFU ex2 ops/s measured "
-                "in this run by ldpc_measure_mufu_peak; the kernel issues 3 MUFU per edge and pass, so "
-                "pipe utilisation = 1.5 x frac",
+        "frac": sfu_achieved / mufu_peak, "traffic": traffic, "traffic_source": traffic_src,
+        "note": "resident kernel (two frames per thread, messages in tensor memory): messages never leave the SM, HBM is "
+                "not the bound; achieved = 2 algorithmic transcendentals per edge and pass / kernel time (CUDA events); "
+                "peak = MUFU ex2 ops/s measured in this run by ldpc_measure_mufu_peak; the kernel issues 3 MUFU per edge "
+                "and pass, so pipe utilisation = 1.5 x frac",
         "mufu_pipe_utilisation": issued_mufu / (kernel_ms * 1e-3) / mufu_peak,
         "kernel_ms": kernel_ms,
+        "smem": {"bound": "smem", "achieved": smem_bytes / (kernel_ms * 1e-3) / 1e9, "peak": smem_peak / 1e9, "unit": "GB/s",
+                 "frac": smem_bytes / (kernel_ms * 1e-3) / smem_peak,
+                 "note": "algorithmic shared-memory bytes (12 + 4 n/E per edge, pass and frame) against 128 B/clk/SM at the "
+                         "sampled SM clock; ncu LSU wavefront share of the same kernel: profiles/"},
         "hbm": {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
     }
+
+    # measured parity of this path against the fp64 oracle (tools/parity_fast.py, committed with the kernel)
+    parity = None
+    par_path = os.path.join(REPO, "profiles", "r2_parity_fast.json")
+    if os.path.exists(par_path):
+        with open(par_path) as f:
+            pr = json.load(f)["regimes"]
+        keep = ("frames", "oracle_converged_fraction", "frame_agree", "frame_agree_converged", "bit_agree", "ok_agree",
+                "conv_agree", "post_rel_median", "post_rel_p99", "post_frames_outside_tolerance", "flips_near_zero")
+        parity = {"source": "profiles/r2_parity_fast.json (tools/parity_fast.py: LDPC_F32_FAST resident kernel vs the fp64 "
+                            "oracle on identical LLRs, 20 passes)",
+                  "bench_workload": {q: pr["bench"].get(q) for q in keep} if "bench" in pr else None,
+                  "converging_regimes_min_frame_agree": min((v["frame_agree"] for kk, v in pr.items()
+                                                             if (v.get("oracle_converged_fraction") or 0) > 0.5), default=None)}
 
     os.sched_setaffinity(0, all_cpus)     # the CPU baseline may use every host core again
     cores = len(all_cpus)
@@ -434,7 +551,7 @@ def main():
     if world == 1:
         sample = args.cpu_frames or 2048 * cores
         rate, secs = cpu_reference_run(sample, cores)
-        cpu = {"value": rate / 1e9, "unit": "Gbit/s", "cores": cores, "kind": "port",
+        cpu = {"value": rate / 1e9, "unit": "Gbit/s", "cores": cores, "kind": "port", "frames": sample,
                "sample": f"{sample} frames of the same workload in {secs:.1f} s, oracle/spa_oracle.c "
                          f"(C port of spa_decoder.py:63-280), {cores} threads"}
 
@@ -443,15 +560,20 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"WiMAX 802.16e n=2304 r1/2 (BASELINE configs[2]): raw ALIST H, QC z=96 resident kernel, "
-                               f"SPA {MAX_ITER} fixed iterations, early termination off, {F} frames per step per GPU, "
-                               f"Philox AWGN LLRs (Eb/N0 {EBN0_DB} dB, all-zero codeword)",
+                               f"SPA {MAX_ITER} fixed iterations, early termination off, {F} frames per step per GPU; "
+                               f"`value` decodes LLRs that were generated beforehand (Philox AWGN, Eb/N0 {EBN0_DB} dB, "
+                               f"all-zero codeword) and are resident in HBM; `mc` generates them inside the kernel",
                    "frames_per_step_per_gpu": F, "l2": "input batch larger than L2 (%.0f MB of LLRs per step)" % (h2d / 1e6),
-                   "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
-                   "converged_fraction": ok_frac},
-        "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                   "parallelism": f"frames sharded over {world} GPU(s); `value`/`e2e`: no data-path collective, "
+                                  f"`mc`: one all-reduce of the counters per interval",
+                   "converged_fraction": ok_frac, "host_cores": cores},
+        "e2e": e2e,
+        "e2e_f16_ingest": e2e16,
+        "mc": mc,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
+        "parity": parity,
         "cpu_baseline": cpu,
     }
     emit(line)

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define LDPC_B200_ABI_VERSION 3
+#define LDPC_B200_ABI_VERSION 4
 
 typedef enum ldpc_status {
     LDPC_OK = 0,
@@ -79,6 +79,12 @@ typedef enum ldpc_dtype {
 #define LDPC_FLAG_PAIR_SCATTER  0x400u /* resident path, two-frames-per-thread kernel: accumulate the posterior in place
                                           (one barrier per group of block rows) instead of the barrier-free check-node
                                           phase + gather (identical results; tests, A/B timing) */
+#define LDPC_FLAG_PAIR_GATHER   0x800u /* resident path: use the two-frames-per-thread gather kernel also with early
+                                          termination (default there: the one-frame kernel) */
+#define LDPC_FLAG_LLR_F16       0x1000u /* ldpc_decode_batch_host only, LDPC_F32 / LDPC_F32_FAST: llr_host holds IEEE half precision
+                                           values (2 bytes per LLR over PCIe instead of 4); they are widened to fp32 on the
+                                           device before decoding.  Not the reference's input type: decisions are those of the
+                                           rounded LLRs (measured agreement: bench.py e2e_f16_ingest) */
 #define LDPC_FLAG_NORM_LLR      0x40u /* ldpc_mc_run: also accumulate the "normalized LLR" metric (spa_decoder.py:210-228)
                                          in counters[5]; runs the generic kernels, which carry the metric */
 
@@ -181,6 +187,10 @@ void ldpc_graph_destroy(ldpc_graph* g);
  * chunk.  A smaller workspace is accepted (frames are then processed in
  * several chunks) down to ldpc_workspace_bytes(g, 32, dtype). */
 size_t ldpc_workspace_bytes(const ldpc_graph* g, int64_t frames, int dtype);
+/* The same for a call with these flags / with a norm_llr_dev output: LDPC_FLAG_FORCE_GENERIC, LDPC_FLAG_NO_JIT,
+ * LDPC_FLAG_TABLE_KERNEL and the normalized-LLR output move an LDPC_F32_FAST call from the resident kernel
+ * (256 bytes) to the generic kernels.  ldpc_workspace_bytes(g, F, t) == ldpc_workspace_bytes_ex(g, F, t, 0, 0). */
+size_t ldpc_workspace_bytes_ex(const ldpc_graph* g, int64_t frames, int dtype, unsigned flags, int want_norm);
 
 /*
  * Decode `frames` frames.  Replaces SPA_Decoder.decode (spa_decoder.py:63-280),
@@ -208,7 +218,8 @@ int ldpc_decode_batch(const ldpc_graph* g, int dtype, int64_t frames, int max_it
  * Same, with HOST buffers: the library stages chunks through pinned memory and
  * overlaps host<->device copies with decoding on its own streams, then blocks
  * until the results are in the host arrays.  This is the end-to-end call
- * behind SPA_Decoder.decode / decode_batch.  z_host may be NULL when only
+ * behind SPA_Decoder.decode / decode_batch.  With LDPC_FLAG_LLR_F16 llr_host is
+ * [frames][n] half precision.  z_host may be NULL when only
  * zbits_host ([frames][4*ceil(n/32)] bytes, bit j of a frame = z[j], LSB first) is wanted.
  */
 int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
@@ -276,6 +287,7 @@ int ldpc_channel_llr_ex(int n, int dtype, int64_t frames, const ldpc_channel* ch
 
 /* Workspace for ldpc_mc_run (it also holds the generated LLRs and decoder outputs). */
 size_t ldpc_mc_workspace_bytes(const ldpc_graph* g, int64_t frames, int dtype);
+size_t ldpc_mc_workspace_bytes_ex(const ldpc_graph* g, int64_t frames, int dtype, unsigned flags);   /* for a call with these flags */
 
 /* Fill llr_dev [frames][n] (float, or double when dtype == LDPC_F64) with the channel
  * output ldpc_mc_run would decode -- used by the tests to feed identical frames to the oracle. */

@@ -15,16 +15,17 @@ LIB_PATH = os.path.join(_HERE, "lib", os.environ.get("LDPC_LIB_NAME", "libldpc_b
 
 LDPC_F64, LDPC_F32, LDPC_F32_FAST = 0, 1, 2
 FLAG_EARLY_TERM, FLAG_COMPACT, FLAG_FIX_ODD_SIGN, FLAG_FORCE_GENERIC, FLAG_TABLE_KERNEL, FLAG_NO_JIT = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
-FLAG_NORM_LLR, FLAG_NO_REPLAY, FLAG_ONE_FRAME, FLAG_PAIR_REGS, FLAG_PAIR_SCATTER = 0x40, 0x80, 0x100, 0x200, 0x400
+FLAG_NORM_LLR, FLAG_NO_REPLAY, FLAG_ONE_FRAME, FLAG_PAIR_REGS, FLAG_PAIR_SCATTER, FLAG_PAIR_GATHER = 0x40, 0x80, 0x100, 0x200, 0x400, 0x800
+FLAG_LLR_F16 = 0x1000
 CHANNEL_SIGMA_SQ, CHANNEL_AMP_07 = 0x1, 0x2
 KERNEL_KINDS = ("generic", "qc_table", "qc_registered", "qc_jit")      # ldpc_kernel_kind
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTS = [
     "ldpc_host_edge_index", "ldpc_host_detect_qc", "ldpc_host_standard_form",
     "ldpc_graph_create_csr", "ldpc_graph_create_qc", "ldpc_graph_info", "ldpc_graph_qc_shifts",
     "ldpc_graph_prepare", "ldpc_host_jit_compile",
-    "ldpc_graph_destroy", "ldpc_workspace_bytes", "ldpc_decode_batch", "ldpc_decode_batch_host",
+    "ldpc_graph_destroy", "ldpc_workspace_bytes", "ldpc_workspace_bytes_ex", "ldpc_mc_workspace_bytes_ex", "ldpc_decode_batch", "ldpc_decode_batch_host",
     "ldpc_mc_run", "ldpc_mc_run_ex", "ldpc_mc_workspace_bytes", "ldpc_channel_llr", "ldpc_channel_llr_ex", "ldpc_encoder_create", "ldpc_encoder_destroy",
     "ldpc_encode_batch", "ldpc_kernel_launch_count",
     "ldpc_measure_mufu_peak", "ldpc_last_error", "ldpc_abi_version",
@@ -79,6 +80,8 @@ def lib():
         "ldpc_host_jit_compile": (C.c_int, [C.c_int, C.c_int, C.c_int, i16p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
         "ldpc_graph_destroy": (None, [vp]),
         "ldpc_workspace_bytes": (C.c_size_t, [vp, i64, C.c_int]),
+        "ldpc_workspace_bytes_ex": (C.c_size_t, [vp, i64, C.c_int, C.c_uint, C.c_int]),
+        "ldpc_mc_workspace_bytes_ex": (C.c_size_t, [vp, i64, C.c_int, C.c_uint]),
         "ldpc_decode_batch": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_uint, vp, vp, vp, vp, vp, vp, C.c_int,
                                         vp, C.c_size_t, vp]),
         "ldpc_decode_batch_host": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_uint, vp, vp, vp, vp, vp, vp, vp, C.c_int]),

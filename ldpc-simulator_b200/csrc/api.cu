@@ -1,6 +1,7 @@
 // api.cu -- extern "C" entry points of include/ldpc_b200.h: argument checks,
 // kernel-path selection, the pinned-memory host pipeline and the Monte-Carlo run.
 #include "ldpc_common.cuh"
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <mutex>
@@ -33,6 +34,7 @@ struct HostSlot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     void* d_llr = nullptr; size_t d_llr_bytes = 0;
+    void* d_llr16 = nullptr; size_t d_llr16_bytes = 0;  // fp16 ingest (LDPC_FLAG_LLR_F16): H2D target, widened into d_llr
     void* d_out = nullptr; size_t d_out_bytes = 0;     // z | zbits | conv | ok | post | norm
     void* d_ws = nullptr; size_t d_ws_bytes = 0;
     void* h_in = nullptr; size_t h_in_bytes = 0;       // pinned staging (pageable callers)
@@ -129,6 +131,21 @@ __global__ void k_pack_bits(const uint8_t* __restrict__ z, int n, int64_t frames
         }
         zbits[id] = v;
     }
+}
+
+// fp16 -> fp32 widening of an LLR chunk on the device (LDPC_FLAG_LLR_F16): 8 values per thread, 128-bit loads
+__global__ void k_widen_llr(const __half* __restrict__ src, float* __restrict__ dst, int64_t count)
+{
+    const int64_t vec = count / 8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < vec; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+        const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c = __half22float2(h[2]), d = __half22float2(h[3]);
+        reinterpret_cast<float4*>(dst)[2 * i] = make_float4(a.x, a.y, b.x, b.y);
+        reinterpret_cast<float4*>(dst)[2 * i + 1] = make_float4(c.x, c.y, d.x, d.y);
+    }
+    for (int64_t i = vec * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = __half2float(src[i]);
 }
 
 int decode_device(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
@@ -274,11 +291,18 @@ __global__ void __launch_bounds__(256) k_mufu_peak(float* sink, int iters)
 }  // namespace
 
 // ---------------------------------------------------------------------------
-extern "C" size_t ldpc_workspace_bytes(const ldpc_graph* g, int64_t frames, int dtype)
+extern "C" size_t ldpc_workspace_bytes_ex(const ldpc_graph* g, int64_t frames, int dtype, unsigned flags, int want_norm)
 {
     if (!g || frames < 0) return 0;
-    if (dtype == LDPC_F32_FAST && qc_resident_kind(g, 0) != LDPC_KERNEL_GENERIC) return 256;
+    // the same decision ldpc_decode_batch takes: the resident kernels need 256 bytes (the work counter of the
+    // early-termination queue), every other combination runs the generic kernels
+    if (use_resident(g, dtype, flags) && !want_norm) return 256;
     return generic_workspace_bytes(g, std::max<int64_t>(frames, 1), dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32);
+}
+
+extern "C" size_t ldpc_workspace_bytes(const ldpc_graph* g, int64_t frames, int dtype)
+{
+    return ldpc_workspace_bytes_ex(g, frames, dtype, 0u, 0);
 }
 
 extern "C" int ldpc_graph_prepare(const ldpc_graph* g, int dtype, unsigned flags, int* kind)
@@ -323,6 +347,9 @@ extern "C" int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t fr
 
     const int n = g->n;
     const size_t esz = dtype == LDPC_F64 ? 8 : 4;
+    const bool in_f16 = (flags & LDPC_FLAG_LLR_F16) != 0;       // the caller's LLRs are IEEE half precision
+    if (in_f16 && dtype == LDPC_F64) { set_error("LDPC_FLAG_LLR_F16 needs LDPC_F32 or LDPC_F32_FAST"); return LDPC_ERR_INVALID; }
+    const size_t esz_in = in_f16 ? 2 : esz;
     const int words = (n + 31) / 32;
     const bool resident = use_resident(g, dtype, flags) && !norm_llr_host;
     const bool need_z_dev = z_host || !resident;       // generic kernels always produce bytes
@@ -333,6 +360,8 @@ extern "C" int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t fr
         const int64_t by_ws = std::max<int64_t>(32, (int64_t)(((size_t)3 << 30) / per32) * 32);
         chunk = std::min(chunk, by_ws);
     }
+    // whole waves of the resident kernels (two CTAs per SM, one or two frames per CTA)
+    if (resident && chunk > 8 * (int64_t)di.sm_count) chunk = chunk / (4 * (int64_t)di.sm_count) * (4 * (int64_t)di.sm_count);
     chunk = std::min<int64_t>((chunk + 31) / 32 * 32, (frames + 31) / 32 * 32);
 
     // output block layout inside one slot (all 256-byte aligned)
@@ -351,7 +380,7 @@ extern "C" int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t fr
 
     std::lock_guard<std::mutex> lk(g_pipe.mu);
     if (!g_pipe.init && (rc = init_pipe())) return rc;
-    if (!resident && frames <= 32 && !(flags & LDPC_FLAG_NO_REPLAY))
+    if (!resident && frames <= 32 && !(flags & LDPC_FLAG_NO_REPLAY) && !in_f16)
         return decode_host_replay(g, dtype, frames, max_iter, flags, llr_host, z_host, zbits_host, conv_iter_host, ok_host,
                                   post_host, norm_llr_host, k_info);
     const int nslots = (int)std::min<int64_t>(kSlots, (frames + chunk - 1) / chunk);
@@ -360,7 +389,8 @@ extern "C" int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t fr
         if ((rc = grow_dev(&sl.d_llr, &sl.d_llr_bytes, (size_t)chunk * n * esz))) return rc;
         if ((rc = grow_dev(&sl.d_out, &sl.d_out_bytes, o_end))) return rc;
         if ((rc = grow_dev(&sl.d_ws, &sl.d_ws_bytes, ws_need))) return rc;
-        if (!in_pinned && (rc = grow_pinned(&sl.h_in, &sl.h_in_bytes, (size_t)chunk * n * esz))) return rc;
+        if (in_f16 && (rc = grow_dev(&sl.d_llr16, &sl.d_llr16_bytes, (size_t)chunk * n * 2))) return rc;
+        if (!in_pinned && (rc = grow_pinned(&sl.h_in, &sl.h_in_bytes, (size_t)chunk * n * esz_in))) return rc;
         if (!out_pinned && (rc = grow_pinned(&sl.h_out, &sl.h_out_bytes, o_end))) return rc;
         sl.busy = false;
     }
@@ -390,10 +420,15 @@ extern "C" int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t fr
         if ((rc = drain(s))) return rc;
         HostSlot& sl = g_pipe.slot[s];
         const int64_t c = std::min<int64_t>(chunk, frames - f0);
-        const char* src = (const char*)llr_host + (size_t)f0 * n * esz;
-        const size_t in_bytes = (size_t)c * n * esz;
+        const char* src = (const char*)llr_host + (size_t)f0 * n * esz_in;
+        const size_t in_bytes = (size_t)c * n * esz_in;
         if (!in_pinned) { staging_copy(sl.h_in, src, in_bytes); src = (const char*)sl.h_in; }
-        LDPC_CUDA_TRY(cudaMemcpyAsync(sl.d_llr, src, in_bytes, cudaMemcpyHostToDevice, sl.stream));
+        LDPC_CUDA_TRY(cudaMemcpyAsync(in_f16 ? sl.d_llr16 : sl.d_llr, src, in_bytes, cudaMemcpyHostToDevice, sl.stream));
+        if (in_f16) {
+            k_widen_llr<<<std::min<int64_t>(((int64_t)c * n / 8 + 255) / 256 + 1, (int64_t)di.sm_count * 8), 256, 0, sl.stream>>>(
+                (const __half*)sl.d_llr16, (float*)sl.d_llr, (int64_t)c * n);
+            LDPC_LAUNCH_CHECK();
+        }
         char* d = (char*)sl.d_out;
         rc = decode_device(g, dtype, c, max_iter, flags, sl.d_llr, need_z_dev ? (uint8_t*)(d + o_z) : nullptr,
                            zbits_host ? (uint32_t*)(d + o_zb) : nullptr, (int32_t*)(d + o_conv), (uint8_t*)(d + o_ok),
@@ -423,8 +458,13 @@ extern "C" int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t fr
 // ---------------------------------------------------------------------------
 extern "C" size_t ldpc_mc_workspace_bytes(const ldpc_graph* g, int64_t frames, int dtype)
 {
+    return ldpc_mc_workspace_bytes_ex(g, frames, dtype, 0u);
+}
+
+extern "C" size_t ldpc_mc_workspace_bytes_ex(const ldpc_graph* g, int64_t frames, int dtype, unsigned flags)
+{
     if (!g || frames < 0) return 0;
-    if (dtype == LDPC_F32_FAST && qc_resident_kind(g, 0) != LDPC_KERNEL_GENERIC) return 256;
+    if (use_resident(g, dtype, flags) && !(flags & LDPC_FLAG_NORM_LLR)) return 256;
     const size_t esz = dtype == LDPC_F64 ? 8 : 4;
     const int64_t F = (std::max<int64_t>(frames, 1) + 31) / 32 * 32;      // ldpc_mc_run works in chunks of 32 frames
     return align_up((size_t)F * g->n * esz, 256) + align_up((size_t)F * g->n, 256) + align_up((size_t)F * 4, 256) * 2 +

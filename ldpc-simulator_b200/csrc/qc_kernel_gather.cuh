@@ -134,6 +134,7 @@ __device__ __forceinline__ void cn_phase(TmemMsgs& ms, const float2* __restrict_
 {
     using R0 = typename TeamRow<TEAM, G0>::type;
     RowMsg<R0::D> m0;
+    ms.begin_pass();
     if constexpr (R0::D > 0) ms.template load<0, 0>(m0, first_pass);
     RowFront2<R0::D> f0;
     row_front2<Z, EARLY>(R0(), m0, post, r, 0, fix_odd, act, ua, ub, f0);
@@ -318,6 +319,7 @@ __device__ __forceinline__ void decode_gather(Code<Z, N, G...>, const float* __r
             }
             tmem_wait_st();
             tmem_st32(ch_addr, chv);
+            ms.template begin_frame_rows<SH::ROWS>();
         }
         __syncthreads();                                 // posterior complete, stage consumed -> prefetch the next pair
         if (use_tma && threadIdx.x == 0 && p_next < pairs)
@@ -343,18 +345,26 @@ __device__ __forceinline__ void decode_gather(Code<Z, N, G...>, const float* __r
                 if (done_a && done_b) break;
                 if (stored) __syncthreads();             // the outputs were read from the posterior the VN phase overwrites
             } else {
+#ifndef LDPC_EXP_NOBAR
                 __syncthreads();                         // every message of this pass is in the edge buffer
+#endif
             }
             uint32_t ch[32];
             tmem_wait_st();
             tmem_ld32(ch_addr, ch);                      // (warp collective: also the lanes without a row)
+#ifdef LDPC_EXP_NOVN
+            if (row_ok && max_iter > 1000) {
+#else
             if (row_ok) {
+#endif
                 if (team == 0) vn_columns<C, 0, 0, G...>(ch, post, ebuf, r);
                 if constexpr (C::TEAMS > 1) { if (team == 1) vn_columns<C, 1, 0, G...>(ch, post, ebuf, r); }
                 if constexpr (C::TEAMS > 2) { if (team == 2) vn_columns<C, 2, 0, G...>(ch, post, ebuf, r); }
                 if constexpr (C::TEAMS > 3) { if (team == 3) vn_columns<C, 3, 0, G...>(ch, post, ebuf, r); }
             }
+#ifndef LDPC_EXP_NOBAR
             __syncthreads();                             // the new posterior is complete
+#endif
         }
 
         // ---- exit: syndrome of the last posterior for the frames that have not converged yet ----

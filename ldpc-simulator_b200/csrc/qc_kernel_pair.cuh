@@ -54,6 +54,8 @@ struct RegMsgs {
 #pragma unroll
         for (int s = 0; s < NS; ++s) eps[s] = f2(0.f, 0.f);
     }
+    template <int ROWS> __device__ __forceinline__ void begin_frame_rows() {}
+    __device__ __forceinline__ void begin_pass() const {}
     template <int EOFF, int ROW, int D>
     __device__ __forceinline__ void load(RowMsg<D>& m, bool) const
     {
@@ -98,20 +100,27 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 struct TmemMsgs {
     static constexpr int ROW_COLS = 16;
     uint32_t taddr0;
+    // the messages of "pass -1" are zero: written once per frame (ROWS stores), so that every pass simply loads
+    template <int ROWS>
+    __device__ __forceinline__ void begin_frame_rows()
+    {
+        uint32_t z[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) z[q] = 0u;
+#pragma unroll
+        for (int row = 0; row < ROWS; ++row) tmem_st16(taddr0 + row * ROW_COLS, z);
+        tmem_wait_st();
+    }
     __device__ __forceinline__ void begin_frame() {}
+    // once per pass, before the first load: this thread's stores of the previous pass have landed
+    __device__ __forceinline__ void begin_pass() const { tmem_wait_st(); }
     template <int EOFF, int ROW, int D>
-    __device__ __forceinline__ void load(RowMsg<D>& m, bool first_pass) const
+    __device__ __forceinline__ void load(RowMsg<D>& m, bool) const
     {
         static_assert(D <= 8, "a row is one 16-column TMEM access");
         uint32_t r[16];
-        if (first_pass) {                     // warp-uniform: the messages of pass -1 are zero
-#pragma unroll
-            for (int q = 0; q < 16; ++q) r[q] = 0u;
-        } else {
-            tmem_wait_st();                   // this thread's store of the previous pass has landed
-            tmem_ld16(taddr0 + ROW * ROW_COLS, r);
-            tmem_wait_ld16(r);
-        }
+        tmem_ld16(taddr0 + ROW * ROW_COLS, r);
+        tmem_wait_ld16(r);
 #pragma unroll
         for (int k = 0; k < D; ++k) m.v[k] = f2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
     }
@@ -298,6 +307,7 @@ __device__ __forceinline__ void team_pass2(MS& ms, float2* __restrict__ sm, cons
 {
     using R0 = typename TeamRow<TEAM, G0>::type;
     RowMsg<R0::D> m0;
+    ms.begin_pass();
     if constexpr (R0::D > 0) ms.template load<0, 0>(m0, first_pass);
     if (phase) mbar_wait(bar, (phase - 1) & 1u);         // the previous pass' posterior is complete
     RowFront2<R0::D> f0;
@@ -516,6 +526,7 @@ __device__ __forceinline__ void decode_pairs(Code<Z, N, G...>, const float* __re
         __syncthreads();
 
         ms.begin_frame();
+        ms.template begin_frame_rows<C::GROUPS>();
 
         int po = 0, no = N;          // pass 0 reads the channel values as the "previous posterior"
         int conv_a = -1, conv_b = -1;

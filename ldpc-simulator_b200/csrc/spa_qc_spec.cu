@@ -182,13 +182,19 @@ int launch_code(C code, const Args& a)
     // request) the one-frame kernel spreads the batch over more SMs.
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
-    const bool pair_ok = !(a.flags & LDPC_FLAG_ONE_FRAME) && a.frames >= 4 * (int64_t)di.sm_count;
-    if constexpr (qc::GatherShape<C>::FITS) if (pair_ok && !(a.flags & (LDPC_FLAG_PAIR_REGS | LDPC_FLAG_PAIR_SCATTER))) {
+    // Kernel choice.  Fixed iteration count (the throughput configuration): two frames per thread, barrier-free
+    // check-node phase + gather (qc_kernel_gather.cuh), 8 % faster than the one-frame kernel.  Early termination: the
+    // one-frame kernel, because a pair iterates until BOTH of its frames are done (E[max] of two iteration counts
+    // costs more than the pair kernel gains).  The LDPC_FLAG_PAIR_* flags force a variant (tests, A/B timing).
+    const bool enough = a.frames >= 4 * (int64_t)di.sm_count;
+    const unsigned forced = a.flags & (LDPC_FLAG_PAIR_REGS | LDPC_FLAG_PAIR_SCATTER | LDPC_FLAG_PAIR_GATHER);
+    const bool pair_ok = !(a.flags & LDPC_FLAG_ONE_FRAME) && enough && (!early || forced);
+    if constexpr (qc::GatherShape<C>::FITS) if (pair_ok && !(forced & (LDPC_FLAG_PAIR_REGS | LDPC_FLAG_PAIR_SCATTER))) {
         constexpr int GB = qc::GatherShape<C>::MINB;
         return early ? launch_gather<C, true, T, GB>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream)
                      : launch_gather<C, false, T, GB>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream);
     }
-    if constexpr (qc::PairShape<C>::TM_ENABLED) if (pair_ok && !(a.flags & LDPC_FLAG_PAIR_REGS)) {
+    if constexpr (qc::PairShape<C>::TM_ENABLED) if (pair_ok && !(forced & LDPC_FLAG_PAIR_REGS)) {
         constexpr int PB = qc::PairShape<C>::TM_MINB;
         return early ? launch_pair<C, true, true, T, PB>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream)
                      : launch_pair<C, false, true, T, PB>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream);

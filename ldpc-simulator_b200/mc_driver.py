@@ -101,17 +101,18 @@ class MonteCarloEngine:
         self.n = int(edd._n)
         self._mask = torch.as_tensor(edd.info_mask(graph)).to(self.device)
         self._ws = None
+        self._ws_capped = False
         self._frame_cursor = 0           # global frame index: keeps Philox counters unique across calls
 
     def _workspace(self, frames):
         torch = self.torch
-        ws_dtype = _native.LDPC_F32 if (self.flags & _native.FLAG_FORCE_GENERIC and self.dtype == _native.LDPC_F32_FAST) else self.dtype
-        need = int(_native.lib().ldpc_mc_workspace_bytes(self.graph.handle, frames, ws_dtype))
+        need = max(256, int(_native.lib().ldpc_mc_workspace_bytes_ex(self.graph.handle, frames, self.dtype, self.flags)))
+        if self._ws is not None and (self._ws.numel() >= need or self._ws_capped):
+            return self._ws                   # (no cudaMemGetInfo on the hot path: it costs milliseconds)
+        self._ws = None
         free_b, _ = torch.cuda.mem_get_info(self.device)
-        need = max(256, min(need, int(free_b * 0.7)))
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = None
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self._ws_capped = need > int(free_b * 0.7)      # the library then works through the frames in chunks
+        self._ws = torch.empty(min(need, max(256, int(free_b * 0.7))), dtype=torch.uint8, device=self.device)
         return self._ws
 
     def codeword(self, rng):
@@ -170,7 +171,7 @@ class MonteCarloEngine:
 
 
 def run_intervals(launch, *, device, rank, world, group, distributed, frames=None, min_frame_errors=None,
-                  max_frames=None, interval_frames=None, frame_cursor=0):
+                  max_frames=None, interval_frames=None, frame_cursor=0, timers=None):
     """Host logic of one SNR point, independent of the device that runs ``launch``.
 
     ``launch(frames_local, counters, frame_offset)`` must accumulate this rank's counters into
@@ -190,11 +191,25 @@ def run_intervals(launch, *, device, rank, world, group, distributed, frames=Non
         chunk = min(interval, budget - done)
         lo, hi = split_frames(chunk, rank, world)
         counters = torch.zeros(6, dtype=torch.int64, device=device)
+        timed = timers is not None and device.type == "cuda"
+        if timed:      # bench.py: where an interval's time goes (CUDA events on the launching stream + wall clock)
+            import time
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            t0 = time.perf_counter()
+            ev[0].record()
         # ranks number their frames from the shared cursor; their Philox streams differ by stream_id = rank
         launch(hi - lo, counters, frame_cursor + lo)
+        if timed:
+            ev[1].record()
         if distributed:
             dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=group)      # the one exchange step
+        if timed:
+            ev[2].record()
         c = counters.cpu().tolist()
+        if timed:
+            wall = time.perf_counter() - t0
+            timers.append({"kernel_ms": ev[0].elapsed_time(ev[1]), "allreduce_us": 1e3 * ev[1].elapsed_time(ev[2]),
+                           "host_us": 1e6 * wall - 1e3 * ev[0].elapsed_time(ev[2])})
         total.frames += c[0]; total.frame_errors += c[1]; total.bit_errors += c[2]
         total.conv_sum += c[3]; total.conv_count += c[4]; total.norm_sum += c[5]
         done += chunk

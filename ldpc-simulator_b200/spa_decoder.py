@@ -127,12 +127,14 @@ class SPA_Decoder:
             flags |= _native.FLAG_PAIR_REGS
         if getattr(s, "is_pair_scatter_kernel", lambda: False)():
             flags |= _native.FLAG_PAIR_SCATTER
+        if getattr(s, "is_pair_gather_kernel", lambda: False)():
+            flags |= _native.FLAG_PAIR_GATHER
         return flags
 
     # ---- batched decode, host buffers (the end-to-end call) -------------------------
     def decode_batch(self, llr, *, precision=None, early_termination=None, compact=None, want_z=True,
                      want_bits=False, want_posterior=False, normalized_llr=None, max_iterations=None,
-                     table_kernel=False, jit=True, replay=True):
+                     table_kernel=False, jit=True, replay=True, llr_f16=False):
         """Decode F frames given as a host array ``llr`` [F, n] (numpy, or a pinned CPU torch tensor).
 
         ``table_kernel`` / ``jit=False`` pick the table-driven resident kernel instead of the one
@@ -140,16 +142,25 @@ class SPA_Decoder:
         Calls of <= 32 frames on the generic kernels are replayed from a CUDA graph captured on the first
         call with the same configuration (``replay=False`` launches the kernels one by one).
 
+        ``llr_f16=True`` (fp32 precisions only; not the reference's input type): ``llr`` is sent to the device in
+        IEEE half precision -- half the PCIe bytes -- and widened to fp32 there (LDPC_FLAG_LLR_F16); a float16
+        array / tensor is taken as is, anything else is rounded to float16 first.
+
         Returns a ``BatchResult`` of host numpy arrays.  Host<->device copies are pipelined inside
         ``ldpc_decode_batch_host`` (pinned staging, several streams).
         """
         g = self.graph
         name, dtype = self._mode(precision)
         ndt = np.float64 if dtype == _native.LDPC_F64 else np.float32
+        odt = ndt                                    # type of the posterior output
+        if llr_f16:
+            if dtype == _native.LDPC_F64:
+                raise ValueError("llr_f16 needs precision 'f32' or 'f32_fast'")
+            ndt = np.float16
         keep = llr                                   # keep the owner alive during the call
         if hasattr(llr, "data_ptr"):                 # torch CPU tensor (possibly pinned)
             import torch
-            want_t = torch.float64 if ndt is np.float64 else torch.float32
+            want_t = {np.float64: torch.float64, np.float32: torch.float32, np.float16: torch.float16}[ndt]
             if llr.device.type != "cpu":
                 raise ValueError("decode_batch takes host buffers; use decode_batch_device for CUDA tensors")
             if llr.dtype != want_t or not llr.is_contiguous():
@@ -173,12 +184,13 @@ class SPA_Decoder:
         zbits = np.empty((frames, words * 4), dtype=np.uint8) if (want_bits or not want_z) else None
         conv = np.empty(frames, dtype=np.int32)
         ok = np.empty(frames, dtype=np.uint8)
-        post = np.empty((frames, n), dtype=ndt) if want_posterior else None
+        post = np.empty((frames, n), dtype=odt) if want_posterior else None
         norm = np.empty(frames, dtype=np.float32) if calc_norm else None
         k_info = int(self.m_pData._n - self.m_pData._m) if calc_norm else 0
         ptr = lambda a: a.ctypes.data if a is not None else None
         _native.check(_native.lib().ldpc_decode_batch_host(
-            g.handle, dtype, frames, int(max_it), self._flags(early_termination, compact, table_kernel, jit, replay), in_ptr,
+            g.handle, dtype, frames, int(max_it),
+            self._flags(early_termination, compact, table_kernel, jit, replay) | (_native.FLAG_LLR_F16 if llr_f16 else 0), in_ptr,
             ptr(z), ptr(zbits), ptr(conv), ptr(ok), ptr(post), ptr(norm), k_info))
         del keep
         return BatchResult(z, zbits, ok, conv, post, norm)
@@ -204,16 +216,17 @@ class SPA_Decoder:
         ok = torch.empty(frames, dtype=torch.uint8, device=dev)
         post = torch.empty((frames, n), dtype=want_t, device=dev) if want_posterior else None
         norm = torch.empty(frames, dtype=torch.float32, device=dev) if normalized_llr else None
+        flags = self._flags(early_termination, compact, table_kernel, jit) | (_native.FLAG_FORCE_GENERIC if force_generic else 0)
         if workspace is None:
-            need = int(_native.lib().ldpc_workspace_bytes(g.handle, frames, dtype))
-            free_b, _tot = torch.cuda.mem_get_info(dev)
-            need = max(min(need, int(free_b * 0.8)), 256)
+            need = int(_native.lib().ldpc_workspace_bytes_ex(g.handle, frames, dtype, flags, int(bool(normalized_llr))))
+            if need > (64 << 20):             # (cudaMemGetInfo costs milliseconds: only when the request is large)
+                free_b, _tot = torch.cuda.mem_get_info(dev)
+                need = min(need, int(free_b * 0.8))
+            need = max(need, 256)
             workspace = torch.empty(need, dtype=torch.uint8, device=dev)
         dp = lambda t: t.data_ptr() if t is not None else None
         _native.check(_native.lib().ldpc_decode_batch(
-            g.handle, dtype, frames, int(max_it),
-            self._flags(early_termination, compact, table_kernel, jit) | (_native.FLAG_FORCE_GENERIC if force_generic else 0),
-            llr.data_ptr(),
+            g.handle, dtype, frames, int(max_it), flags, llr.data_ptr(),
             z.data_ptr(), conv.data_ptr(), ok.data_ptr(), dp(post), dp(norm),
             int(self.m_pData._n - self.m_pData._m), workspace.data_ptr(), workspace.numel(),
             torch.cuda.current_stream(dev).cuda_stream))

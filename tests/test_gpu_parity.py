@@ -561,7 +561,8 @@ def test_pair_kernel_is_bit_identical_to_the_one_frame_kernel(name, frames, earl
     llr = awgn_llr(rng, frames, code.n, np.resize(np.array([1.0, 1.6, 2.2, 3.0]), frames)).astype(np.float32)
     # gather (the default): barrier-free check-node phase + gather variable-node phase, messages in tensor memory;
     # scatter_tmem / scatter_regs: in-place posterior accumulation with the messages in tensor memory / registers
-    kw = {"gather": {}, "scatter_tmem": {"pair_scatter_kernel": True}, "scatter_regs": {"pair_regs_kernel": True}}[variant]
+    kw = {"gather": {"pair_gather_kernel": True}, "scatter_tmem": {"pair_scatter_kernel": True},
+          "scatter_regs": {"pair_regs_kernel": True}}[variant]
     pair = make_decoder(code, 20, "f32_fast", fix_odd_check_sign=fix, **kw).decode_batch(
         llr, want_posterior=True, want_bits=True, early_termination=early)
     one = make_decoder(code, 20, "f32_fast", fix_odd_check_sign=fix, one_frame_kernel=True).decode_batch(
@@ -589,6 +590,43 @@ def test_pair_kernel_monte_carlo_counters_equal_the_one_frame_kernel():
         counters = torch.zeros(5, dtype=torch.int64, device="cuda")
         eng.launch(5001, 0.5, 1.6, counters, frame_offset=3)
         return counters.cpu().tolist()
-    a, b, c, d = run(0), run(_native.FLAG_ONE_FRAME), run(_native.FLAG_PAIR_REGS), run(_native.FLAG_PAIR_SCATTER)
-    assert a == b == c == d
+    a, b, c, d = run(_native.FLAG_PAIR_GATHER), run(_native.FLAG_ONE_FRAME), run(_native.FLAG_PAIR_REGS), run(_native.FLAG_PAIR_SCATTER)
+    assert a == b == c == d == run(0)
     assert a[0] == 5001 and 0 < a[1] < 5001
+
+
+def test_default_workspace_covers_the_generic_fallbacks_of_the_fast_precision():
+    """ldpc_workspace_bytes_ex follows the kernel choice of the call: LDPC_F32_FAST on a quasi-cyclic graph needs
+    256 bytes on the resident kernel but a generic workspace with force_generic or a normalized-LLR output."""
+    import torch
+    code = load_code("wimax_576_0.5")
+    rng = np.random.default_rng(5)
+    llr = torch.as_tensor(awgn_llr(rng, 300, code.n, 2.0).astype(np.float32)).cuda()
+    dec = make_decoder(code, 10, "f32_fast")
+    a = dec.decode_batch_device(llr)
+    b = dec.decode_batch_device(llr, force_generic=True)
+    c = dec.decode_batch_device(llr, normalized_llr=True)
+    assert c.norm is not None and c.norm.shape == (300,)
+    assert (a.ok == b.ok).float().mean() > 0.99 and torch.equal(b.ok, c.ok) and torch.equal(b.z, c.z)
+
+
+def test_fp16_llr_ingest_decodes_the_rounded_llrs():
+    """LDPC_FLAG_LLR_F16: the host sends half precision LLRs; the result must be exactly that of decoding the
+    rounded values sent as fp32 (the widening on the device is exact), for pinned torch and pageable numpy input."""
+    import torch
+    code = load_code("wimax_2304_0.5")
+    rng = np.random.default_rng(16)
+    llr = awgn_llr(rng, 3000, code.n, 2.0).astype(np.float32)
+    half = llr.astype(np.float16)
+    dec = make_decoder(code, 20, "f32_fast", fix_odd_check_sign=True)
+    want = dec.decode_batch(half.astype(np.float32), want_posterior=True, want_bits=True)
+    got = dec.decode_batch(half, llr_f16=True, want_posterior=True, want_bits=True)
+    pinned = torch.as_tensor(half).pin_memory()
+    got2 = dec.decode_batch(pinned, llr_f16=True, want_posterior=True, want_bits=True)
+    for g in (got, got2):
+        assert np.array_equal(g.z, want.z) and np.array_equal(g.ok, want.ok) and np.array_equal(g.conv_it, want.conv_it)
+        assert np.array_equal(g.post, want.post) and np.array_equal(g.zbits, want.zbits)
+    full = dec.decode_batch(llr)
+    assert (full.ok == want.ok).mean() > 0.995          # rounding the channel values to 11 bits barely moves the decoder
+    with pytest.raises(ValueError):
+        make_decoder(code, 20, "f64").decode_batch(half, llr_f16=True)
