@@ -167,9 +167,17 @@ def run_reference_arm(args):
     return 0
 
 
-def run_parity576(args):
-    """Auxiliary line: BASELINE configs[1] (WiMAX-576 r1/2, raw ALIST H, fp64 parity kernels, 65 536 frames,
-    20 passes) -- the HBM-streaming generic path, reported against the measured HBM copy bandwidth."""
+GENERIC_WORKLOADS = {
+    # name: (code fixture, frames, BASELINE config it stands for, two-sweep check nodes)
+    "parity576": ("wimax_576_0.5", 65536, "BASELINE configs[1]: WiMAX-576 r1/2, raw ALIST H (E = 1 824)", False),
+    "std576": ("wimax_576_0.5.std", 8192, "config 1' = what main.py really decodes: WiMAX-576 r1/2 on H_std (E = 41 278, check degree 96-192)", True),
+    "std2304": ("wimax_2304_0.5.std", 2048, "config 2' = what main.py really decodes: WiMAX-2304 r1/2 on H_std (E = 663 172, check degree 416-632)", True),
+}
+
+
+def run_generic(args):
+    """Auxiliary lines: the HBM-streaming generic path (fp64 parity kernels, 20 passes, early termination as the
+    reference has it), reported against the measured HBM copy bandwidth."""
     import torch
     import _native
     from channel import Channel
@@ -177,7 +185,8 @@ def run_parity576(args):
     from spa_decoder import SPA_Decoder
     from scipy import sparse
     torch.cuda.set_device(0)
-    d = np.load(os.path.join(REPO, "tests", "golden", "codes", "wimax_576_0.5.npz"))
+    fixture, F, label, two_sweep = GENERIC_WORKLOADS[args.workload]
+    d = np.load(os.path.join(REPO, "tests", "golden", "codes", fixture + ".npz"))
     m, n = int(d["m"]), int(d["n"])
     h = sparse.csr_matrix((np.ones(d["col_idx"].size, dtype=np.int32), d["col_idx"], d["row_ptr"]), shape=(m, n))
 
@@ -187,38 +196,42 @@ def run_parity576(args):
 
     st = Settings(); st.set_max_iterations(MAX_ITER); st.set_precision("f64")
     dec = SPA_Decoder(Edd(), st)
-    F = 65536
     ch = Channel.create_channel(SPEED, EBN0_DB, 0.0, 1, 0.1, 1)
     ch.sigma_sq_quirk = False
     llr = ch.device_llr(F, n, seed=0x5EED, dtype="f64")
     ws = torch.empty(int(_native.lib().ldpc_workspace_bytes(dec.graph.handle, F, _native.LDPC_F64)), dtype=torch.uint8, device="cuda")
-    for _ in range(max(args.warmup, 3)):
-        dec.decode_batch_device(llr, workspace=ws)
+    warm = max(args.warmup, 3)
+    steps = args.steps if args.workload == "parity576" else min(args.steps, 5)
+    for _ in range(warm):
+        out = dec.decode_batch_device(llr, workspace=ws)
     torch.cuda.synchronize()
     l0 = _native.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        dec.decode_batch_device(llr, workspace=ws)
+    for _ in range(steps):
+        out = dec.decode_batch_device(llr, workspace=ws)
     e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
+    ms = e0.elapsed_time(e1) / steps
     E = dec.graph.nnz
-    alg = F * MAX_ITER * (24 * E + 26 * n) + F * n * (8 + 8 + 1)          # DESIGN.md 4.1 + load/store transposes
+    per_pass = 24 * E + 26 * n + (16 * E if two_sweep else 0)
+    alg = F * MAX_ITER * per_pass + F * n * (8 + 8 + 1)               # + load/store transposes
     peak = 6650.0
     pp = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(pp):
         peak = float(json.load(open(pp))["hbm_gbs"])
-    line = {"metric": "decoded_info_gbit_per_s_20_spa_iters_wimax_n576_r12_fp64_parity_kernels", "value": F * (n - m) / (ms * 1e-3) / 1e9,
-            "unit": "Gbit/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+    line = {"metric": "decoded_info_gbit_per_s_20_spa_iters_%s_fp64_parity_kernels" % args.workload,
+            "value": F * (n - m) / (ms * 1e-3) / 1e9,
+            "unit": "Gbit/s", "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": ms,
             "higher_is_better": True, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "WiMAX 802.16e n=576 r1/2 (BASELINE configs[1]), raw ALIST H, fp64 generic kernels, "
-                                   "65536 frames per step, 20 passes, working set %.1f GB (> L2)" % (F * (2 * E + 2 * n) * 8 / 1e9)},
+            "config": {"workload": "%s; fp64 generic kernels, %d frames per step, %d passes, working set %.1f GB (> L2); "
+                                   "converged fraction %.3f" % (label, F, MAX_ITER, F * (2 * E + 2 * n) * 8 / 1e9, float(out.ok.float().mean()))},
             "gpu_launches": int(_native.launches() - l0),
             "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                          "note": "whole step (check-node + variable-node + syndrome kernels x 20 passes), algorithmic bytes "
-                                 "24E+26n per pass and frame in fp64 (three message sweeps); the check-node kernel is bound by "
-                                 "fp64 tanh/atanh issue, not by HBM (ncu: FP64 pipe 44 %, issue slots 69 % busy)"}}
+                                 "24E+26n per pass and frame in fp64 (three message sweeps)%s; the check-node kernel is bound by "
+                                 "fp64 tanh/atanh issue, not by HBM (ncu: FP64 pipe 44 %%, issue slots 69 %% busy)"
+                                 % (" + 16E for the second sweep of rows that do not fit the registers" if two_sweep else "")}}
     emit(line)
     return 0
 
@@ -251,14 +264,15 @@ def main():
     ap.add_argument("--spin", type=float, default=1.0, help="seconds of untimed load before the timed region (after the warm-up steps)")
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=0, help="cpu_baseline sample size (0 = 2048 x cores)")
-    ap.add_argument("--workload", default="throughput", choices=["throughput", "parity576"],
-                    help="throughput: the headline (configs[2]); parity576: configs[1], fp64 generic kernels, "
-                         "HBM roofline of the streaming path (auxiliary line, not the headline)")
+    ap.add_argument("--workload", default="throughput", choices=["throughput", "parity576", "std576", "std2304"],
+                    help="throughput: the headline (configs[2]); parity576 / std576 / std2304: the fp64 generic kernels on "
+                         "configs[1] and on the dense H_std graphs main.py really decodes -- HBM roofline of the streaming "
+                         "path (auxiliary lines, not the headline)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
-    if args.workload == "parity576":
-        return run_parity576(args)
+    if args.workload != "throughput":
+        return run_generic(args)
     args.warmup = max(args.warmup, 3)
 
     import torch

@@ -155,8 +155,16 @@ int decode_device(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, 
     if (frames == 0) return LDPC_OK;
     if (use_resident(g, dtype, flags) && !norm) {
         McParams mc;
-        return qc_resident_decode(g, frames, max_iter, flags, (const float*)llr, z, zbits, conv, ok,
-                                  (float*)post, mc, ws, ws_bytes, stream);
+        const int rc = qc_resident_decode(g, frames, max_iter, flags, (const float*)llr, z, zbits, conv, ok,
+                                          (float*)post, mc, ws, ws_bytes, stream);
+        // a run-time specialisation that failed downgrades the handle to the generic kernels (spa_qc_resident.cu):
+        // carry on with them when the caller's buffers allow it
+        if (rc != LDPC_ERR_UNSUPPORTED || use_resident(g, dtype, flags)) return rc;
+        if (ws_bytes < generic_workspace_bytes(g, 32, LDPC_F32)) {
+            set_error("the resident kernel could not be specialised for this code; the generic kernels need the workspace "
+                      "ldpc_workspace_bytes_ex now reports");
+            return LDPC_ERR_WORKSPACE;
+        }
     }
     // LDPC_F32_FAST on a graph without a resident kernel (or with LDPC_FLAG_FORCE_GENERIC): the generic
     // kernels with MUFU arithmetic in the check node
@@ -310,8 +318,10 @@ extern "C" int ldpc_graph_prepare(const ldpc_graph* g, int dtype, unsigned flags
     if (!g) { set_error("null graph"); return LDPC_ERR_INVALID; }
     int k = use_resident(g, dtype, flags) ? qc_resident_kind(g, flags) : LDPC_KERNEL_GENERIC;
     if (k == LDPC_KERNEL_QC_JIT && qc_jit_prepare(g) != LDPC_OK) {
-        if (!qc_resident_supported(g)) return LDPC_ERR_UNSUPPORTED;     // message set by qc_jit_prepare
-        k = LDPC_KERNEL_QC_TABLE;
+        // no NVRTC / compile error: the handle is downgraded for good (same rule as in qc_resident_decode) -- the
+        // table-driven kernel where it has a shape for the code, else the generic kernels
+        k = qc_resident_supported(g) ? LDPC_KERNEL_QC_TABLE : LDPC_KERNEL_GENERIC;
+        g->kind_cache[0].store(k, std::memory_order_relaxed);
     }
     if (kind) *kind = k;
     return LDPC_OK;

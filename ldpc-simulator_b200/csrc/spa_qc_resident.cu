@@ -430,8 +430,13 @@ int qc_resident_decode(const ldpc_graph* g, int64_t frames, int max_iter, unsign
     if (kind == LDPC_KERNEL_QC_JIT) {
         const int rc = qc_jit_decode(g, frames, max_iter, flags, llr_dev, z_dev, zbits_dev, conv_dev, ok_dev, post_dev,
                                      mc, ws, stream);
-        // a failed specialisation (remembered per code) leaves the table-driven kernel where it applies
-        if (rc != LDPC_ERR_UNSUPPORTED || !qc_resident_supported(g)) return rc;
+        if (rc != LDPC_ERR_UNSUPPORTED) return rc;
+        // The specialisation failed (no NVRTC, compile error; remembered per code by qc_jit.cu): downgrade the memoised
+        // kernel family of this handle, so that ldpc_workspace_bytes_ex / ldpc_graph_prepare / later calls see what will
+        // really run -- the table-driven kernel where it has a shape for the code, else the generic kernels.
+        const bool table = qc_resident_supported(g);
+        g->kind_cache[0].store(table ? LDPC_KERNEL_QC_TABLE : LDPC_KERNEL_GENERIC, std::memory_order_relaxed);
+        if (!table) return rc;             // decode_device falls through to the generic kernels
     }
     Outputs out{z_dev, zbits_dev, conv_dev, ok_dev, post_dev};
     switch (pick_shape(g)) {

@@ -240,9 +240,19 @@ class SPA_Decoder:
         res = self.decode_batch(llr[None, :], want_posterior=False, normalized_llr=calc_norm)
         p_data_buffer._decoded_data = res.z[0].astype(np.int32).tolist()
         if calc_norm:
-            # the reference appends one value per pass (:227-228); only the exit value, the one
-            # consumers read (:237-239, main.py:332-334), is produced here
+            # The reference appends one count and one value per executed pass (:226-228) and leaves the last one in
+            # _d_summarize_normalized_llr (:237-239,249-251).  The kernels produce the value of the EXIT pass; the value
+            # after pass p is the exit value of the same decode cut off after p+1 passes (early termination cannot
+            # strike earlier: the frame has not converged before its exit pass), so the history is p short decodes.
+            passes = (int(res.conv_it[0]) + 1) if res.ok[0] else int(self.m_pSettings.get_max_iterations())
+            k = int(self.m_pData._n - self.m_pData._m)
+            for p in range(1, passes):
+                part = self.decode_batch(llr[None, :], want_z=False, want_bits=True, normalized_llr=True, max_iterations=p)
+                value = float(part.norm[0])
+                self._arr_changed_by_iterations.append(int(round(value * k)))
+                self._normalized_llr_by_iterations.append(value)
             value = float(res.norm[0])
+            self._arr_changed_by_iterations.append(int(round(value * k)))
             self._normalized_llr_by_iterations.append(value)
             self._d_summarize_normalized_llr = value
         if res.ok[0]:

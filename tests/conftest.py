@@ -85,7 +85,9 @@ def load_golden(name):
 
 GOLDEN_DECODE_SETS = ["bch74_std_random", "ccsds128_alist", "ccsds128_std", "tanner155_std", "wifi648_alist",
                       "wimax576_alist", "wimax576_alist_cw", "wimax576_std", "wimax2304_alist",
-                      "wimax2304_075B_alist", "wimax2304_083_alist", "wimax2304_std"]
+                      "wimax2304_075B_alist", "wimax2304_083_alist", "wimax2304_std",
+                      # round 2: a thicker live-reference pin (2 048 / 256 frames; H_std of the headline code, 20 passes)
+                      "wimax576_alist_2k", "wimax2304_alist_256", "wimax2304_std_20it"]
 
 
 def posterior_violations(got, ref, rel=1e-4, abs_tol=1e-5):

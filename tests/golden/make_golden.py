@@ -271,8 +271,11 @@ def _mixed_llrs(rng, n, frames, snrs, speed, quirk, codewords=None):
 
 
 def build_decode_set(tag, graph_name, frames, snrs, speed, quirk, max_iter, seed, jobs,
-                     calc_norm=False, random_codewords=False):
-    """Seeded frames through the unmodified reference decoder on the named graph."""
+                     calc_norm=False, random_codewords=False, store_f32=False):
+    """Seeded frames through the unmodified reference decoder on the named graph.
+
+    ``store_f32`` (the large sets): the LLRs are rounded to float32 BEFORE the reference decodes them, so the
+    file can hold them -- and the posteriors -- in single precision without changing what was decoded."""
     gpath = os.path.join(CODES_DIR, graph_name + ".npz")
     d = np.load(gpath)
     n, m = int(d["n"]), int(d["m"])
@@ -295,8 +298,12 @@ def build_decode_set(tag, graph_name, frames, snrs, speed, quirk, max_iter, seed
             codewords = np.zeros_like(cw_std)
             codewords[:, perm] = cw_std            # H_std[:, j] = H[:, perm[j]]
     llr, snr_of = _mixed_llrs(rng, n, frames, snrs, speed, quirk, codewords)
+    if store_f32:
+        llr = llr.astype(np.float32).astype(np.float64)
     t0 = time.time()
     z, ok, conv, post, norm, passes = decode_many(gpath, llr, max_iter, calc_norm, jobs)
+    if store_f32:
+        llr, post = llr.astype(np.float32), post.astype(np.float32)
     extra = {}
     if data is not None:
         extra = dict(data=data, codeword=codewords)
@@ -385,6 +392,34 @@ def build_w576_mc_anchor(jobs):
             f"BER {p['bit_err']/(288*p['frames']):.5f}")
         with open(os.path.join(HERE, "wimax576_std_mc_anchor.json"), "w") as f:
             json.dump(dict(speed=0.5, max_iter=20, k=288, n=576, points=pts), f, indent=1, sort_keys=True)
+
+
+def build_norm_history():
+    """Per-pass history of the "normalized LLR" metric (spa_decoder.py:210-228): the lists SPA_Decoder leaves in
+    _arr_changed_by_iterations / _normalized_llr_by_iterations after one decode(), for a few seeded frames."""
+    from scipy import sparse
+    from spa_decoder import SPA_Decoder
+    out = {}
+    for graph_name, frames, snrs, max_iter, seed in [("ccsds_128_64", 12, [1.0, 2.5, 4.0], 20, 901), ("bch_7_4.std", 8, [0.0, 3.0], 50, 902)]:
+        d = np.load(os.path.join(CODES_DIR, graph_name + ".npz"))
+        n, m = int(d["n"]), int(d["m"])
+        h = sparse.csr_matrix((np.ones(d["col_idx"].size, dtype=np.int32), d["col_idx"], d["row_ptr"]), shape=(m, n))
+        rng = np.random.default_rng(seed)
+        llr, snr_of = _mixed_llrs(rng, n, frames, snrs, 0.5, False)
+        rows = []
+        for f in range(frames):
+            settings = _make_spy_settings(max_iter, True)
+            dec = SPA_Decoder(_GraphOnly(h), settings)
+            buf = _Frame(llr[f])
+            dec.decode(buf)
+            rows.append(dict(llr=[float(x) for x in llr[f]], conv_it=int(dec.convergence_iteration),
+                             changed=[int(x) for x in dec._arr_changed_by_iterations],
+                             normalized=[float(x) for x in dec._normalized_llr_by_iterations],
+                             summary=float(dec._d_summarize_normalized_llr)))
+        out[graph_name] = dict(max_iter=max_iter, frames=rows)
+        log(f"norm history {graph_name}: passes {[len(r['changed']) for r in rows]}")
+    with open(os.path.join(HERE, "norm_history.json"), "w") as fh:
+        json.dump(out, fh)
 
 
 def build_results_sample():
@@ -510,6 +545,7 @@ def main():
         "stdform": build_stdform,
         "bch_kat": build_bch_kat,
         "results": build_results_sample,
+        "norm_history": build_norm_history,
         "adaptive": build_adaptive_strategy,
         "channel_modes": build_channel_modes,
         "catalog": build_catalog_listing,
@@ -542,6 +578,13 @@ def main():
                                               0.83, False, 20, 230404, J),
         "w2304_std": lambda: build_decode_set("wimax2304_std", "wimax_2304_0.5.std", 8, [5, 6],
                                               0.5, True, 2, 230403, J),
+        # round 2: a thicker live-reference pin
+        "w576_alist_2k": lambda: build_decode_set("wimax576_alist_2k", "wimax_576_0.5", 2048, [1, 2, 3, 4, 6],
+                                                  0.5, False, 20, 20261019, J, store_f32=True),
+        "w2304_alist_256": lambda: build_decode_set("wimax2304_alist_256", "wimax_2304_0.5", 256, [1, 2, 3, 6],
+                                                    0.5, False, 20, 230411, J, store_f32=True),
+        "w2304_std_20": lambda: build_decode_set("wimax2304_std_20it", "wimax_2304_0.5.std", 8, [4, 5, 6, 7],
+                                                 0.5, True, 20, 230413, J, random_codewords=True),
         "bch_mc": lambda: build_bch_mc_anchor(J),
         "w576_mc": lambda: build_w576_mc_anchor(J),
     }

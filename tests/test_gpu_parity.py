@@ -128,7 +128,8 @@ def test_config1_full_batch_64k_frames_against_oracle():
     ref_s = oracle(std, sub, 20)
     res_s = make_decoder(std, 20).decode_batch(sub, want_posterior=True)
     assert frame_mismatch(res_s, ref_s).mean() <= 1e-4
-    assert posterior_violations(res_s.post, ref_s["post"]).any(axis=1).mean() <= 1e-3
+    viol_s = posterior_violations(res_s.post, ref_s["post"]).any(axis=1)
+    assert viol_s.mean() <= 1e-4, f"{viol_s.sum()} of 4096 frames outside the posterior tolerance on H_std"
 
 
 def test_compaction_and_chunking_do_not_change_results():
@@ -231,6 +232,11 @@ def test_fp32_paths_against_the_fp64_oracle(precision, name, frames):
     agree = 1.0 - frame_mismatch(res, ref).mean()
     bit_agree = (res.z == ref["z"]).mean()
     print(f"{precision} {name}: frame agreement {agree:.4f}, bit agreement {bit_agree:.6f}")
+    if precision == "f32_fast":
+        # measured (profiles/r2_parity_fast.json): 10 of 65 536 non-converging frames differ, each in one bit whose
+        # posterior is within 3e-6 of zero
+        assert bit_agree > 0.999999
+        assert agree > 0.998
     assert bit_agree > 0.999
     assert agree > 0.97
     err = np.abs(res.post - ref["post"]) / np.maximum(np.abs(ref["post"]), 1.0)
@@ -479,7 +485,8 @@ def test_early_termination_on_large_codes():
     assert 0.05 < ref["ok"].mean() < 0.999 and ref["conv_it"].max() > 5
     g64 = make_decoder(code, 20, "f64").decode_batch(llr, compact=True, want_posterior=True)
     assert not frame_mismatch(g64, ref).any()
-    assert posterior_violations(g64.post, ref["post"]).any(axis=1).mean() <= 1e-3
+    viol = posterior_violations(g64.post, ref["post"]).any(axis=1)
+    assert viol.mean() <= 1e-4, f"{viol.sum()} of 2048 frames outside the posterior tolerance"
     for table in (False, True):
         fast = make_decoder(code, 20, "f32_fast").decode_batch(llr.astype(np.float32), table_kernel=table)
         assert (fast.ok == ref["ok"]).mean() > 0.99 and (fast.z == ref["z"]).mean() > 0.9995
@@ -630,3 +637,93 @@ def test_fp16_llr_ingest_decodes_the_rounded_llrs():
     assert (full.ok == want.ok).mean() > 0.995          # rounding the channel values to 11 bits barely moves the decoder
     with pytest.raises(ValueError):
         make_decoder(code, 20, "f64").decode_batch(half, llr_f16=True)
+
+
+# ---- measured parity of the throughput path (BASELINE north_star: >= 99.99 % of frames bit-exact) ----
+@pytest.mark.parametrize("regime,frames", [("fix_1.5dB", 16384), ("fix_2.0dB", 16384), ("r083_3.5dB", 16384), ("fix_6dB", 8192)])
+def test_fast_path_frames_agree_with_the_oracle_where_it_converges(regime, frames):
+    """LDPC_F32_FAST resident kernels vs the fp64 oracle on identical LLRs, regimes in which the reference's
+    decoder converges (tools/parity_fast.py lists them): decisions, syndrome result AND iteration-at-convergence
+    identical on >= 99.99 % of ALL frames (measured: every frame), posterior of the exit pass inside the
+    north-star tolerance on >= 98 % of the frames (the rest: |L| > 30, where the reference's own fp64 tanh
+    rounding is larger than the tolerance)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
+    import parity_fast as pf
+    fixture, rate, ebn0, fix, _ = pf.REGIMES[regime]
+    code = load_code(fixture)
+    llr = pf.llr_batch(4242, frames, code.n, ebn0, rate)
+    ref = oracle(code, llr.astype(np.float64), 20, fix_odd_check_sign=fix)
+    for kw in ({}, {"pair_gather_kernel": True}):        # early termination: one-frame kernel / forced gather kernel
+        res = make_decoder(code, 20, "f32_fast", fix_odd_check_sign=fix, **kw).decode_batch(llr, want_posterior=True)
+        r = pf.compare(res, ref, code.n)
+        print(regime, kw, {k: r[k] for k in ("oracle_converged_fraction", "frame_agree", "post_frames_outside_tolerance")})
+        assert r["oracle_converged_fraction"] > 0.5
+        assert r["frame_agree"] >= 0.9999
+        assert r["conv_agree"] >= 0.9999 and r["ok_agree"] >= 0.9999
+        assert r["post_frames_outside_tolerance"] <= 0.02
+
+
+def test_fast_path_on_the_bench_workload_differs_only_where_a_posterior_is_zero():
+    """The timed configuration (reference sign convention, 2 dB, 20 fixed passes: nothing converges, the
+    trajectories are chaotic): syndrome and iteration agree on every frame, and a hard decision may differ from
+    the fp64 oracle only where the oracle's posterior is within 1e-5 of zero (north_star: "any disagreement is
+    only allowed where an LLR sits within tolerance of zero")."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
+    import parity_fast as pf
+    code = load_code("wimax_2304_0.5")
+    llr = pf.llr_batch(777, 16384, code.n, 2.0, 0.5)
+    ref = oracle(code, llr.astype(np.float64), 20)
+    res = make_decoder(code, 20, "f32_fast").decode_batch(llr, want_posterior=True, early_termination=False)
+    assert np.array_equal(res.ok, ref["ok"]) and np.array_equal(res.conv_it, ref["conv_it"])
+    flips = res.z != ref["z"]
+    assert flips.mean() < 1e-6
+    if flips.any():
+        assert np.abs(ref["post"][flips]).max() <= 1e-5
+    rel = np.abs(res.post - ref["post"]) / np.maximum(np.abs(ref["post"]), 1.0)
+    assert np.median(rel) < 1e-6 and np.quantile(rel, 0.99) < 1e-5
+
+
+def test_per_pass_normalized_llr_history_through_the_per_frame_api():
+    """SPA_Decoder.decode leaves one count / one value per executed pass in _arr_changed_by_iterations /
+    _normalized_llr_by_iterations (spa_decoder.py:226-228); pinned on lists written by the unmodified reference."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from data_buffer import DataBuffer
+    with open(os.path.join(GOLDEN, "norm_history.json")) as f:
+        hist = json.load(f)
+    for graph_name, entry in hist.items():
+        code = load_code(graph_name)
+        for row in entry["frames"]:
+            dec = make_decoder(code, int(entry["max_iter"]), normalized_llr_calculate=True)
+            buf = DataBuffer(0)
+            buf._channel_data = list(row["llr"])
+            dec.decode(buf)
+            assert dec.convergence_iteration == row["conv_it"]
+            assert dec._arr_changed_by_iterations == row["changed"]
+            np.testing.assert_allclose(dec._normalized_llr_by_iterations, row["normalized"], atol=1e-7)
+            assert abs(dec._d_summarize_normalized_llr - row["summary"]) < 1e-7
+
+
+def test_headline_kernel_against_the_live_reference_on_the_headline_code():
+    """tests/golden/wimax2304_alist_256.npz: 256 frames decoded by the UNMODIFIED reference on the raw WiMAX-2304 graph
+    (Eb/N0 1/2/3/6 dB, 20 passes, nothing converges under its sign convention).  The fp32 resident kernels must give the
+    same syndrome / iteration for every frame and the same decisions except where the reference's posterior is within
+    tolerance of zero or its own fp64 tanh has saturated (|L| > 30 at 6 dB)."""
+    d = load_golden("wimax2304_alist_256")
+    code = load_code(str(d["graph"]))
+    llr = np.asarray(d["llr"], dtype=np.float32)
+    low = d["snr_db"] < 5.0
+    for kw in ({}, {"one_frame_kernel": True}):
+        res = make_decoder(code, int(d["max_iter"]), "f32_fast", **kw).decode_batch(
+            np.tile(llr, (3, 1)), want_posterior=True, early_termination=False)      # 768 frames: the pair kernel runs
+        for rep in range(3):
+            sl = slice(rep * 256, rep * 256 + 256)
+            assert np.array_equal(res.ok[sl], d["ok"]) and np.array_equal(res.conv_it[sl], d["conv_it"])
+            flips = res.z[sl] != d["z"]
+            assert flips[low].sum() <= 2 and (not flips[low].any() or np.abs(d["post"][low][flips[low]]).max() < 1e-4)
+            assert flips.mean() < 1e-4
+            rel = np.abs(res.post[sl] - d["post"]) / np.maximum(np.abs(d["post"]), 1.0)
+            assert np.median(rel[low]) < 1e-6 and np.quantile(rel[low], 0.999) < 1e-4
