@@ -440,6 +440,23 @@ def main():
              "note": "LLRs rounded to IEEE half on the host, widened to fp32 on the device; this workload (reference sign "
                      "convention, 2 dB) never converges, so its decisions are those of a chaotic trajectory"}
     del llr_host16
+    # int8 fixed-point LLRs (LDPC_FLAG_LLR_I8, LLR = q / 4): a quarter of the fp32 bytes; a QUANTISED input, labelled
+    from spa_decoder import quantize_llr_i8
+    llr_host8 = torch.empty((F, n), dtype=torch.int8).pin_memory()
+    llr_host8.copy_(quantize_llr_i8(llr_dev))
+
+    def step_host8():
+        return dec.decode_batch(llr_host8, want_z=False, want_bits=True, llr_i8=True)
+
+    t_8, t8_ranks, res8 = timed_host(step_host8)
+    e2e8 = {"value": world * F * k * args.steps / t_8 / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": F * n,
+            "d2h_bytes_per_step": d2h, "h2d_gbs_whole_job": world * F * n * args.steps / t_8 / 1e9,
+            "per_rank_gbit_s": [F * k * args.steps / t / 1e9 for t in t8_ranks],
+            "decision_bit_agreement_vs_fp32_ingest": float(1.0 - np.unpackbits(res8.zbits ^ res32.zbits).mean() * words * 32 / n),
+            "syndrome_agreement_vs_fp32_ingest": float((res8.ok == res32.ok).mean()),
+            "note": "LLRs quantised on the host to int8, q = round(4 LLR) clipped to +-127, widened on the device; same "
+                    "non-converging workload as above, so the decision agreement compares two chaotic trajectories"}
+    del llr_host8
 
     # ---- the Monte-Carlo path: in-kernel Philox channel + decode + counters, one all-reduce per interval ----
     from encoder_decoder_data import EncoderDecoderData
@@ -583,6 +600,7 @@ def main():
                    "converged_fraction": ok_frac, "host_cores": cores},
         "e2e": e2e,
         "e2e_f16_ingest": e2e16,
+        "e2e_i8_ingest": e2e8,
         "mc": mc,
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -148,6 +148,22 @@ __global__ void k_widen_llr(const __half* __restrict__ src, float* __restrict__ 
         dst[i] = __half2float(src[i]);
 }
 
+// int8 fixed point -> fp32 (LDPC_FLAG_LLR_I8: LLR = q / 4): 16 values per thread
+__global__ void k_widen_llr_i8(const int8_t* __restrict__ src, float* __restrict__ dst, int64_t count)
+{
+    const int64_t vec = count / 16;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < vec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int4 raw = __ldg(reinterpret_cast<const int4*>(src) + i);
+        const int w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            reinterpret_cast<float4*>(dst)[4 * i + q] = make_float4(0.25f * (float)(int8_t)(w[q] & 0xff), 0.25f * (float)(int8_t)((w[q] >> 8) & 0xff),
+                                                                    0.25f * (float)(int8_t)((w[q] >> 16) & 0xff), 0.25f * (float)(int8_t)(w[q] >> 24));
+    }
+    for (int64_t i = vec * 16 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = 0.25f * (float)src[i];
+}
+
 int decode_device(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
                   const void* llr, uint8_t* z, uint32_t* zbits, int32_t* conv, uint8_t* ok, void* post,
                   float* norm, int k_info, void* ws, size_t ws_bytes, cudaStream_t stream)
@@ -357,9 +373,11 @@ extern "C" int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t fr
 
     const int n = g->n;
     const size_t esz = dtype == LDPC_F64 ? 8 : 4;
-    const bool in_f16 = (flags & LDPC_FLAG_LLR_F16) != 0;       // the caller's LLRs are IEEE half precision
-    if (in_f16 && dtype == LDPC_F64) { set_error("LDPC_FLAG_LLR_F16 needs LDPC_F32 or LDPC_F32_FAST"); return LDPC_ERR_INVALID; }
-    const size_t esz_in = in_f16 ? 2 : esz;
+    const bool in_i8 = (flags & LDPC_FLAG_LLR_I8) != 0;         // the caller's LLRs are int8 fixed point, LLR = q / 4
+    const bool in_f16 = (flags & LDPC_FLAG_LLR_F16) != 0 || in_i8;   // (narrow ingest: H2D into d_llr16, widened on the device)
+    if (in_f16 && dtype == LDPC_F64) { set_error("LDPC_FLAG_LLR_F16 / LDPC_FLAG_LLR_I8 need LDPC_F32 or LDPC_F32_FAST"); return LDPC_ERR_INVALID; }
+    if (in_i8 && (flags & LDPC_FLAG_LLR_F16)) { set_error("LDPC_FLAG_LLR_F16 and LDPC_FLAG_LLR_I8 exclude each other"); return LDPC_ERR_INVALID; }
+    const size_t esz_in = in_i8 ? 1 : in_f16 ? 2 : esz;
     const int words = (n + 31) / 32;
     const bool resident = use_resident(g, dtype, flags) && !norm_llr_host;
     const bool need_z_dev = z_host || !resident;       // generic kernels always produce bytes
@@ -435,8 +453,9 @@ extern "C" int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t fr
         if (!in_pinned) { staging_copy(sl.h_in, src, in_bytes); src = (const char*)sl.h_in; }
         LDPC_CUDA_TRY(cudaMemcpyAsync(in_f16 ? sl.d_llr16 : sl.d_llr, src, in_bytes, cudaMemcpyHostToDevice, sl.stream));
         if (in_f16) {
-            k_widen_llr<<<std::min<int64_t>(((int64_t)c * n / 8 + 255) / 256 + 1, (int64_t)di.sm_count * 8), 256, 0, sl.stream>>>(
-                (const __half*)sl.d_llr16, (float*)sl.d_llr, (int64_t)c * n);
+            const int wgrid = (int)std::min<int64_t>(((int64_t)c * n / 8 + 255) / 256 + 1, (int64_t)di.sm_count * 8);
+            if (in_i8) k_widen_llr_i8<<<wgrid, 256, 0, sl.stream>>>((const int8_t*)sl.d_llr16, (float*)sl.d_llr, (int64_t)c * n);
+            else k_widen_llr<<<wgrid, 256, 0, sl.stream>>>((const __half*)sl.d_llr16, (float*)sl.d_llr, (int64_t)c * n);
             LDPC_LAUNCH_CHECK();
         }
         char* d = (char*)sl.d_out;

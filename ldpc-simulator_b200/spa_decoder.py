@@ -29,6 +29,14 @@ from matrix_sparse import DeviceGraph
 _PRECISIONS = {"f64": _native.LDPC_F64, "f32": _native.LDPC_F32, "f32_fast": _native.LDPC_F32_FAST}
 
 
+def quantize_llr_i8(llr):
+    """LLRs -> the int8 fixed-point format of LDPC_FLAG_LLR_I8: q = round(4 LLR), clipped to [-127, 127]."""
+    if hasattr(llr, "data_ptr"):
+        import torch
+        return torch.clamp(torch.round(llr.to(torch.float32) * 4.0), -127, 127).to(torch.int8)
+    return np.clip(np.rint(np.asarray(llr, dtype=np.float32) * 4.0), -127, 127).astype(np.int8)
+
+
 class BatchResult:
     """Outputs of ``decode_batch``: arrays over frames."""
     __slots__ = ("z", "zbits", "ok", "conv_it", "post", "norm")
@@ -134,7 +142,7 @@ class SPA_Decoder:
     # ---- batched decode, host buffers (the end-to-end call) -------------------------
     def decode_batch(self, llr, *, precision=None, early_termination=None, compact=None, want_z=True,
                      want_bits=False, want_posterior=False, normalized_llr=None, max_iterations=None,
-                     table_kernel=False, jit=True, replay=True, llr_f16=False):
+                     table_kernel=False, jit=True, replay=True, llr_f16=False, llr_i8=False):
         """Decode F frames given as a host array ``llr`` [F, n] (numpy, or a pinned CPU torch tensor).
 
         ``table_kernel`` / ``jit=False`` pick the table-driven resident kernel instead of the one
@@ -144,7 +152,8 @@ class SPA_Decoder:
 
         ``llr_f16=True`` (fp32 precisions only; not the reference's input type): ``llr`` is sent to the device in
         IEEE half precision -- half the PCIe bytes -- and widened to fp32 there (LDPC_FLAG_LLR_F16); a float16
-        array / tensor is taken as is, anything else is rounded to float16 first.
+        array / tensor is taken as is, anything else is rounded to float16 first.  ``llr_i8=True``: int8 fixed point
+        q = round(4 LLR) clipped to +-127 (``quantize_llr_i8``), a quarter of the bytes (LDPC_FLAG_LLR_I8).
 
         Returns a ``BatchResult`` of host numpy arrays.  Host<->device copies are pipelined inside
         ``ldpc_decode_batch_host`` (pinned staging, several streams).
@@ -153,14 +162,18 @@ class SPA_Decoder:
         name, dtype = self._mode(precision)
         ndt = np.float64 if dtype == _native.LDPC_F64 else np.float32
         odt = ndt                                    # type of the posterior output
-        if llr_f16:
+        if llr_f16 or llr_i8:
             if dtype == _native.LDPC_F64:
-                raise ValueError("llr_f16 needs precision 'f32' or 'f32_fast'")
-            ndt = np.float16
+                raise ValueError("llr_f16 / llr_i8 need precision 'f32' or 'f32_fast'")
+            if llr_f16 and llr_i8:
+                raise ValueError("llr_f16 and llr_i8 exclude each other")
+            ndt = np.float16 if llr_f16 else np.int8
+            if llr_i8 and not (hasattr(llr, "dtype") and str(llr.dtype) in ("int8", "torch.int8")):
+                llr = quantize_llr_i8(llr)
         keep = llr                                   # keep the owner alive during the call
         if hasattr(llr, "data_ptr"):                 # torch CPU tensor (possibly pinned)
             import torch
-            want_t = {np.float64: torch.float64, np.float32: torch.float32, np.float16: torch.float16}[ndt]
+            want_t = {np.float64: torch.float64, np.float32: torch.float32, np.float16: torch.float16, np.int8: torch.int8}[ndt]
             if llr.device.type != "cpu":
                 raise ValueError("decode_batch takes host buffers; use decode_batch_device for CUDA tensors")
             if llr.dtype != want_t or not llr.is_contiguous():
@@ -190,7 +203,7 @@ class SPA_Decoder:
         ptr = lambda a: a.ctypes.data if a is not None else None
         _native.check(_native.lib().ldpc_decode_batch_host(
             g.handle, dtype, frames, int(max_it),
-            self._flags(early_termination, compact, table_kernel, jit, replay) | (_native.FLAG_LLR_F16 if llr_f16 else 0), in_ptr,
+            self._flags(early_termination, compact, table_kernel, jit, replay) | (_native.FLAG_LLR_F16 if llr_f16 else 0) | (_native.FLAG_LLR_I8 if llr_i8 else 0), in_ptr,
             ptr(z), ptr(zbits), ptr(conv), ptr(ok), ptr(post), ptr(norm), k_info))
         del keep
         return BatchResult(z, zbits, ok, conv, post, norm)

@@ -635,6 +635,15 @@ def test_fp16_llr_ingest_decodes_the_rounded_llrs():
         assert np.array_equal(g.post, want.post) and np.array_equal(g.zbits, want.zbits)
     full = dec.decode_batch(llr)
     assert (full.ok == want.ok).mean() > 0.995          # rounding the channel values to 11 bits barely moves the decoder
+    # int8 fixed point (LDPC_FLAG_LLR_I8, LLR = q / 4): exactly the decode of the dequantised values
+    from spa_decoder import quantize_llr_i8
+    q = quantize_llr_i8(llr)
+    want8 = dec.decode_batch(q.astype(np.float32) * 0.25, want_posterior=True)
+    got8 = dec.decode_batch(q, llr_i8=True, want_posterior=True)
+    got8b = dec.decode_batch(llr, llr_i8=True, want_posterior=True)          # quantised by the call
+    for g in (got8, got8b):
+        assert np.array_equal(g.z, want8.z) and np.array_equal(g.conv_it, want8.conv_it) and np.array_equal(g.post, want8.post)
+    assert (got8.ok == full.ok).mean() > 0.98
     with pytest.raises(ValueError):
         make_decoder(code, 20, "f64").decode_batch(half, llr_f16=True)
 
@@ -727,3 +736,20 @@ def test_headline_kernel_against_the_live_reference_on_the_headline_code():
             assert flips.mean() < 1e-4
             rel = np.abs(res.post[sl] - d["post"]) / np.maximum(np.abs(d["post"]), 1.0)
             assert np.median(rel[low]) < 1e-6 and np.quantile(rel[low], 0.999) < 1e-4
+
+
+def test_resident_kernels_are_deterministic_and_identical():
+    """Stand-in for racecheck (compute-sanitizer is closed on this pool): repeated runs of every resident variant are
+    bit-identical, and the variants -- which synchronise differently -- agree bit for bit with each other."""
+    code = load_code("wimax_2304_0.5")
+    rng = np.random.default_rng(314)
+    llr = awgn_llr(rng, 2368 + 1, code.n, np.resize(np.array([1.5, 2.0, 3.0]), 2369)).astype(np.float32)
+    outs = []
+    for kw in ({"pair_gather_kernel": True}, {"pair_scatter_kernel": True}, {"pair_regs_kernel": True}, {"one_frame_kernel": True}):
+        dec = make_decoder(code, 20, "f32_fast", fix_odd_check_sign=True, **kw)
+        runs = [dec.decode_batch(llr, want_posterior=True) for _ in range(3)]
+        for r in runs[1:]:
+            assert np.array_equal(r.post, runs[0].post) and np.array_equal(r.conv_it, runs[0].conv_it)
+        outs.append(runs[0])
+    for o in outs[1:]:
+        assert np.array_equal(o.post, outs[0].post) and np.array_equal(o.z, outs[0].z) and np.array_equal(o.conv_it, outs[0].conv_it)
