@@ -310,6 +310,8 @@ def main():
     st.set_early_termination(False)
     if os.environ.get("LDPC_BENCH_ONE_FRAME"):      # A/B: the one-frame-per-thread resident kernel
         st.set_one_frame_kernel(True)
+    if os.environ.get("LDPC_BENCH_ONE_GATHER"):     # A/B: one-frame gather kernel, tensor-memory messages, 4 CTAs per SM
+        st.set_one_gather_kernel(True)
     if os.environ.get("LDPC_BENCH_PAIR_SCATTER"):   # A/B: pair kernel, in-place posterior accumulation, messages in TMEM
         st.set_pair_scatter_kernel(True)
     if os.environ.get("LDPC_BENCH_PAIR_REGS"):      # A/B: pair kernel with the messages in registers instead of TMEM

@@ -88,6 +88,8 @@ typedef enum ldpc_dtype {
 #define LDPC_FLAG_LLR_I8        0x2000u /* ldpc_decode_batch_host only, fp32 precisions: llr_host holds int8 fixed-point values q,
                                            LLR = q / 4 (range +-31.75, step 0.25; 1 byte per LLR over PCIe), widened on the
                                            device.  A quantised input, labelled as such wherever it is measured */
+#define LDPC_FLAG_ONE_GATHER    0x4000u /* resident path: one frame per thread with the gather structure and tensor-memory
+                                           messages (four CTAs per SM); identical results */
 #define LDPC_FLAG_NORM_LLR      0x40u /* ldpc_mc_run: also accumulate the "normalized LLR" metric (spa_decoder.py:210-228)
                                          in counters[5]; runs the generic kernels, which carry the metric */
 

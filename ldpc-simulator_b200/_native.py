@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", os.environ.get("LDPC_LIB_NAME", "libldpc_b
 LDPC_F64, LDPC_F32, LDPC_F32_FAST = 0, 1, 2
 FLAG_EARLY_TERM, FLAG_COMPACT, FLAG_FIX_ODD_SIGN, FLAG_FORCE_GENERIC, FLAG_TABLE_KERNEL, FLAG_NO_JIT = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 FLAG_NORM_LLR, FLAG_NO_REPLAY, FLAG_ONE_FRAME, FLAG_PAIR_REGS, FLAG_PAIR_SCATTER, FLAG_PAIR_GATHER = 0x40, 0x80, 0x100, 0x200, 0x400, 0x800
-FLAG_LLR_F16, FLAG_LLR_I8 = 0x1000, 0x2000
+FLAG_LLR_F16, FLAG_LLR_I8, FLAG_ONE_GATHER = 0x1000, 0x2000, 0x4000
 CHANNEL_SIGMA_SQ, CHANNEL_AMP_07 = 0x1, 0x2
 KERNEL_KINDS = ("generic", "qc_table", "qc_registered", "qc_jit")      # ldpc_kernel_kind
 ABI_VERSION = 4

@@ -92,8 +92,10 @@ __device__ __forceinline__ void row_emit(Row<S...>, const RowMsg<sizeof...(S)>& 
     constexpr int D = sizeof...(S);
     if constexpr (D == 0) return;
     if (!act) return;
+#ifndef LDPC_EXP_NOSMEM
 #pragma unroll
     for (int k = 0; k < D; ++k) ebuf[(slot0 + k) * Z + r] = m.v[k];
+#endif
 }
 
 template <int Z, int TEAM, int TBASE, int EOFF, int ROW, bool EARLY, class GCUR>
@@ -352,7 +354,7 @@ __device__ __forceinline__ void decode_gather(Code<Z, N, G...>, const float* __r
             uint32_t ch[32];
             tmem_wait_st();
             tmem_ld32(ch_addr, ch);                      // (warp collective: also the lanes without a row)
-#ifdef LDPC_EXP_NOVN
+#if defined(LDPC_EXP_NOVN) || defined(LDPC_EXP_NOSMEM)
             if (row_ok && max_iter > 1000) {
 #else
             if (row_ok) {

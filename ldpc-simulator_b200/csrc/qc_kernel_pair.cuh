@@ -164,7 +164,11 @@ __device__ __forceinline__ void row_front2(Row<S...>, RowMsg<sizeof...(S)>& m, c
     for (int c = 0; c < D; ++c) {
         int idx = r + SH[c];
         idx = (int)min((unsigned)idx, (unsigned)(idx - Z));      // (r + shift) mod z
+#ifdef LDPC_EXP_NOSMEM      // timing experiment (wrong results): no shared-memory traffic in the check-node phase
+        const float2 L = f2((float)(idx + c) * 0.01f, (float)(idx - c) * 0.02f);
+#else
         const float2 L = act ? sm[po + CB[c] + idx] : f2(1.f, 1.f);
+#endif
         const float2 mu = f2sub(L, m.v[c]);                      // variable->check messages, :260-268
         if (EARLY) { par_a ^= (L.x < 0.f); par_b ^= (L.y < 0.f); }
         m.v[c] = mu;                                             // parked until row_back2 (signs)

@@ -6,6 +6,7 @@
 #include "qc_codes_gen.cuh"
 #include "qc_kernel_pair.cuh"
 #include "qc_kernel_gather.cuh"
+#include "qc_kernel_gather1.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -167,6 +168,41 @@ int launch_gather(C code, const ldpc_graph* g, int64_t frames, int max_iter, uns
     return LDPC_OK;
 }
 
+// One frame per thread, gather structure, tensor-memory messages (qc_kernel_gather1.cuh): up to four CTAs per SM.
+template <class C, bool EARLY, int THREADS, int MINB>
+int launch_gather1(C code, const ldpc_graph* g, int64_t frames, int max_iter, unsigned flags, const float* llr,
+                   const qc::Outputs& out, const McParams& mc, void* ws, cudaStream_t stream)
+{
+    using SH = qc::Gather1Shape<C>;
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc) return rc;
+    auto kp = qc::k_qc_gather1<THREADS, MINB, EARLY, C>;
+    const size_t smem = std::max(SH::SMEM, (size_t)di.max_smem_optin / (SH::MAX_CTAS + 1) + 1024);
+    if (smem > (size_t)di.max_smem_optin) { set_error("gather1 kernel: %zu bytes of shared memory do not fit", smem); return LDPC_ERR_UNSUPPORTED; }
+    static KernelConfig kc;
+    int per_sm = 0;
+    if ((rc = configure(kp, kc, di.device, THREADS, smem, &per_sm)) != LDPC_OK) return rc;
+    if (per_sm < 1) { set_error("gather1 resident kernel does not fit on an SM"); return LDPC_ERR_UNSUPPORTED; }
+    if (per_sm > SH::MAX_CTAS) { set_error("internal: TMEM occupancy cap not effective"); return LDPC_ERR_UNSUPPORTED; }
+    if (const char* force = getenv("LDPC_PAIR_PER_SM")) per_sm = atoi(force);      // tuning experiments only
+    const int grid = (int)std::min<int64_t>(frames, (int64_t)per_sm * di.sm_count);
+    if (getenv("LDPC_TRACE_LAUNCH"))
+        fprintf(stderr, "[ldpc] gather1 kernel early=%d threads=%d smem=%zu per_sm=%d grid=%d frames=%lld\n", (int)EARLY,
+                THREADS, smem, per_sm, grid, (long long)frames);
+    unsigned long long* counter = nullptr;
+    if (EARLY) {
+        if (!ws) { set_error("early termination needs a workspace (work counter)"); return LDPC_ERR_WORKSPACE; }
+        counter = (unsigned long long*)ws;
+        LDPC_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+    }
+    (void)code;
+    kp<<<grid, THREADS, smem, stream>>>(llr, out, (long long)frames, max_iter,
+                                        (flags & LDPC_FLAG_FIX_ODD_SIGN) ? 1 : 0, mc, counter);
+    LDPC_LAUNCH_CHECK();
+    return LDPC_OK;
+}
+
 struct Args {
     const ldpc_graph* g; int64_t frames; int max_iter; unsigned flags; const float* llr; qc::Outputs out;
     const McParams* mc; void* ws; cudaStream_t stream;
@@ -186,6 +222,11 @@ int launch_code(C code, const Args& a)
     // check-node phase + gather (qc_kernel_gather.cuh), 8 % faster than the one-frame kernel.  Early termination: the
     // one-frame kernel, because a pair iterates until BOTH of its frames are done (E[max] of two iteration counts
     // costs more than the pair kernel gains).  The LDPC_FLAG_PAIR_* flags force a variant (tests, A/B timing).
+    if constexpr (qc::Gather1Shape<C>::FITS) if (a.flags & LDPC_FLAG_ONE_GATHER) {
+        constexpr int GB = qc::Gather1Shape<C>::MINB;
+        return early ? launch_gather1<C, true, T, GB>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream)
+                     : launch_gather1<C, false, T, GB>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream);
+    }
     const bool enough = a.frames >= 4 * (int64_t)di.sm_count;
     const unsigned forced = a.flags & (LDPC_FLAG_PAIR_REGS | LDPC_FLAG_PAIR_SCATTER | LDPC_FLAG_PAIR_GATHER);
     const bool pair_ok = !(a.flags & LDPC_FLAG_ONE_FRAME) && enough && (!early || forced);

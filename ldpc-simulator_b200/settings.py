@@ -29,6 +29,7 @@ class Settings:
         self._pair_regs_kernel = False     # resident path: pair kernel with the messages in registers, not TMEM
         self._pair_scatter_kernel = False  # resident path: pair kernel with in-place posterior accumulation (TMEM messages)
         self._pair_gather_kernel = False   # resident path: gather pair kernel also with early termination
+        self._one_gather_kernel = False    # resident path: one-frame gather kernel (tensor-memory messages, 4 CTAs per SM)
 
     # -- reference surface ----------------------------------------------------
     def set_blocks_cnt(self, i_num_blocks): self._i_blocks_cnt = i_num_blocks
@@ -78,3 +79,5 @@ class Settings:
     def is_pair_scatter_kernel(self): return self._pair_scatter_kernel
     def set_pair_gather_kernel(self, flag): self._pair_gather_kernel = bool(flag)
     def is_pair_gather_kernel(self): return self._pair_gather_kernel
+    def set_one_gather_kernel(self, flag): self._one_gather_kernel = bool(flag)
+    def is_one_gather_kernel(self): return self._one_gather_kernel

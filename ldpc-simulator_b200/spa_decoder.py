@@ -137,6 +137,8 @@ class SPA_Decoder:
             flags |= _native.FLAG_PAIR_SCATTER
         if getattr(s, "is_pair_gather_kernel", lambda: False)():
             flags |= _native.FLAG_PAIR_GATHER
+        if getattr(s, "is_one_gather_kernel", lambda: False)():
+            flags |= _native.FLAG_ONE_GATHER
         return flags
 
     # ---- batched decode, host buffers (the end-to-end call) -------------------------

@@ -554,7 +554,7 @@ def test_frame_order_and_batch_split_invariance():
 
 
 # ---- two-frames-per-thread resident kernel (csrc/qc_kernel_pair.cuh) --------------------------------
-@pytest.mark.parametrize("variant", ["gather", "scatter_tmem", "scatter_regs"])
+@pytest.mark.parametrize("variant", ["gather", "scatter_tmem", "scatter_regs", "one_gather"])
 @pytest.mark.parametrize("name,frames,early,fix", [
     ("wimax_2304_0.5", 4096, False, False), ("wimax_2304_0.5", 4097, True, True), ("wimax_2304_0.5", 1999, True, False),
     ("wimax_576_0.5", 3001, True, True), ("wimax_576_0.5", 2048, False, False),
@@ -569,7 +569,7 @@ def test_pair_kernel_is_bit_identical_to_the_one_frame_kernel(name, frames, earl
     # gather (the default): barrier-free check-node phase + gather variable-node phase, messages in tensor memory;
     # scatter_tmem / scatter_regs: in-place posterior accumulation with the messages in tensor memory / registers
     kw = {"gather": {"pair_gather_kernel": True}, "scatter_tmem": {"pair_scatter_kernel": True},
-          "scatter_regs": {"pair_regs_kernel": True}}[variant]
+          "scatter_regs": {"pair_regs_kernel": True}, "one_gather": {"one_gather_kernel": True}}[variant]
     pair = make_decoder(code, 20, "f32_fast", fix_odd_check_sign=fix, **kw).decode_batch(
         llr, want_posterior=True, want_bits=True, early_termination=early)
     one = make_decoder(code, 20, "f32_fast", fix_odd_check_sign=fix, one_frame_kernel=True).decode_batch(
@@ -598,7 +598,7 @@ def test_pair_kernel_monte_carlo_counters_equal_the_one_frame_kernel():
         eng.launch(5001, 0.5, 1.6, counters, frame_offset=3)
         return counters.cpu().tolist()
     a, b, c, d = run(_native.FLAG_PAIR_GATHER), run(_native.FLAG_ONE_FRAME), run(_native.FLAG_PAIR_REGS), run(_native.FLAG_PAIR_SCATTER)
-    assert a == b == c == d == run(0)
+    assert a == b == c == d == run(0) == run(_native.FLAG_ONE_GATHER)
     assert a[0] == 5001 and 0 < a[1] < 5001
 
 
@@ -745,7 +745,8 @@ def test_resident_kernels_are_deterministic_and_identical():
     rng = np.random.default_rng(314)
     llr = awgn_llr(rng, 2368 + 1, code.n, np.resize(np.array([1.5, 2.0, 3.0]), 2369)).astype(np.float32)
     outs = []
-    for kw in ({"pair_gather_kernel": True}, {"pair_scatter_kernel": True}, {"pair_regs_kernel": True}, {"one_frame_kernel": True}):
+    for kw in ({"pair_gather_kernel": True}, {"pair_scatter_kernel": True}, {"pair_regs_kernel": True}, {"one_gather_kernel": True},
+               {"one_frame_kernel": True}):
         dec = make_decoder(code, 20, "f32_fast", fix_odd_check_sign=True, **kw)
         runs = [dec.decode_batch(llr, want_posterior=True) for _ in range(3)]
         for r in runs[1:]:

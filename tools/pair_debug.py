@@ -12,8 +12,11 @@ class Edd:
     def __init__(self, h): self._h_sparse_cached, (self._m, self._n) = h, h.shape
 
 code = load_code(sys.argv[1] if len(sys.argv) > 1 else "wimax_2304_0.5")
+VARIANT = os.environ.get("PAIR_DEBUG_VARIANT", "")        # e.g. one_gather_kernel
 def dec(it, one):
     st = Settings(); st.set_max_iterations(it); st.set_precision("f32_fast"); st.set_early_termination(False); st.set_one_frame_kernel(one)
+    if VARIANT and not one:
+        getattr(st, "set_" + VARIANT)(True)
     return SPA_Decoder(Edd(code.csr()), st)
 rng = np.random.default_rng(3)
 F = 2048

@@ -48,7 +48,7 @@ def main():
         for name, frames in [("wimax_2304_0.5", 701), ("wimax_576_0.5", 1190)]:
             code = load_code(name)
             llr = rng.normal(-1.0, 2.0, size=(frames, code.n)).astype(np.float32)
-            for variant in ("pair_gather_kernel", "pair_scatter_kernel", "pair_regs_kernel"):
+            for variant in ("pair_gather_kernel", "pair_scatter_kernel", "pair_regs_kernel", "one_gather_kernel"):
                 st = Settings()
                 st.set_max_iterations(4)
                 st.set_precision("f32_fast")
