@@ -180,7 +180,7 @@ __device__ __forceinline__ void row_front2(Row<S...>, RowMsg<sizeof...(S)>& m, c
     if (EARLY) { unsat_a |= par_a; unsat_b |= par_b; }
 }
 
-// Back half: leave-one-out products with packed FMAs, |E| = lg2 A - lg2 B (2 x 2 MUFU.LG2), signs.
+// Back half: leave-one-out products with packed FMAs, |E| = lg2(A / B) with one reciprocal per two edges, signs.
 // (The expressions are those of row_back in qc_kernel.cuh, lane by lane.)
 template <class... S>
 __device__ __forceinline__ void row_back2(Row<S...>, RowMsg<sizeof...(S)>& m, const RowFront2<sizeof...(S)>& f)
@@ -204,6 +204,8 @@ __device__ __forceinline__ void row_back2(Row<S...>, RowMsg<sizeof...(S)>& m, co
         }
     }
     float2 sa = one, sb = f2(0.f, 0.f);      // suffix product over slots > k
+    float2 heldA = one, heldB = one;         // first edge of a pair, waiting for its partner
+    int heldk = 0;
 #pragma unroll
     for (int k = D - 1; k >= 0; --k) {
         float2 A, B;
@@ -219,12 +221,32 @@ __device__ __forceinline__ void row_back2(Row<S...>, RowMsg<sizeof...(S)>& m, co
             A = f2fma(fa[k - 1], sa, f2mul(fb[k - 1], sb));
             B = f2fma(fa[k - 1], sb, f2mul(fb[k - 1], sa));
         }
-        const float2 mag = f2sub(f2(lg2_approx(A.x), lg2_approx(A.y)),
-                                 f2(lg2_approx(B.x), lg2_approx(B.y)));    // |E| in bits, :151-168
-        const uint32_t sa_bit = (f.sgn_a ^ __float_as_uint(m.v[k].x)) & 0x80000000u;
-        const uint32_t sb_bit = (f.sgn_b ^ __float_as_uint(m.v[k].y)) & 0x80000000u;
-        m.v[k] = f2(__uint_as_float(__float_as_uint(mag.x) | sa_bit),
-                    __uint_as_float(__float_as_uint(mag.y) | sb_bit));
+        // |E| = lg2(A / B) (:151-168).  The quotients of TWO edges share one reciprocal, 1 / (B_h B): 2.5 instead of 3
+        // MUFU per edge (B >= 6e-16 by the clip on |m|, so the product of two stays a normal number).  Edges are
+        // paired in the order they are finished (k = D-1 with D-2, D-3 with D-4, ...); an odd row leaves k = 0 alone.
+        {
+            const bool second = ((D - 1 - k) & 1) != 0;
+            if (!second && k > 0) { heldA = A; heldB = B; heldk = k; }
+            else {
+                float2 Rh = one, R;
+                if (second) {
+                    const float2 P = f2mul(heldB, B);
+                    const float2 rp = f2(rcp_approx(P.x), rcp_approx(P.y));
+                    Rh = f2mul(heldA, f2mul(rp, B));
+                    R = f2mul(A, f2mul(rp, heldB));
+                    const float2 mg = f2(lg2_approx(Rh.x), lg2_approx(Rh.y));
+                    const uint32_t s1 = (f.sgn_a ^ __float_as_uint(m.v[heldk].x)) & 0x80000000u;
+                    const uint32_t s2 = (f.sgn_b ^ __float_as_uint(m.v[heldk].y)) & 0x80000000u;
+                    m.v[heldk] = f2(__uint_as_float(__float_as_uint(mg.x) | s1), __uint_as_float(__float_as_uint(mg.y) | s2));
+                } else {
+                    R = f2mul(A, f2(rcp_approx(B.x), rcp_approx(B.y)));
+                }
+                const float2 mag = f2(lg2_approx(R.x), lg2_approx(R.y));
+                const uint32_t sa_bit = (f.sgn_a ^ __float_as_uint(m.v[k].x)) & 0x80000000u;
+                const uint32_t sb_bit = (f.sgn_b ^ __float_as_uint(m.v[k].y)) & 0x80000000u;
+                m.v[k] = f2(__uint_as_float(__float_as_uint(mag.x) | sa_bit), __uint_as_float(__float_as_uint(mag.y) | sb_bit));
+            }
+        }
         if (k == D - 1) { sb = f.x[k]; }     // sa stays 1
         else if (k == D - 2) {
             sa = f2fma(sb, f.x[k], one);
