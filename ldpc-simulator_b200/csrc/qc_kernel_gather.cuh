@@ -9,8 +9,9 @@
 //
 // Here a pass is split the way the reference writes it (spa_decoder.py:112-185):
 //   CN phase   every thread walks its block rows back to back WITHOUT synchronisation: previous posterior
-//              (LDS.64) - own previous message (tensor memory) -> likelihood-ratio check node -> new messages
-//              to tensor memory (for the next pass) and to the edge buffer E[slot][row] in shared memory
+//              (LDS.64, rotated) - own previous message (LDS.64 of the thread's own word of the edge buffer: the
+//              variable-node phase only reads it, so it still holds the messages of the previous pass) ->
+//              likelihood-ratio check node -> new messages to the edge buffer E[slot][row] in shared memory
 //              (STS.64, the thread's own word: no address arithmetic, no conflict);
 //   barrier
 //   VN phase   every thread owns column r of some of the block columns: posterior = channel value (tensor
@@ -21,8 +22,10 @@
 // the same order as in the scatter kernels, so the results are bit-identical to them (tested).
 //
 // Shared memory per CTA (float2 units): posterior [n] | edge buffer [edges of the base matrix][z] | TMA stage
-// (2 n floats); the channel values live in tensor memory, next to the messages (per thread: GROUPS rows of 16
-// columns + 32 columns of channel values).
+// (2 n floats); the channel values of the columns a thread owns live in tensor memory (32 columns per thread, one
+// tcgen05.ld per pass).  Round 2 first kept the messages in tensor memory as well (one tcgen05.ld/st of 16 columns per
+// row): reading them back from the edge buffer costs one LDS.64 per edge more but drops the LDTM/STTM, their waits
+// and the register shuffling around the 16-register blocks -- 16.81 instead of 17.09 ms (profiles/r2_tuning.md).
 #pragma once
 #include "qc_kernel_pair.cuh"
 
@@ -65,9 +68,7 @@ struct GatherShape {
     static constexpr int WARPS = THREADS / 32;
     static constexpr int NB = C::N / C::Z;                                   // block columns
     static constexpr int OWN = (NB + C::TEAMS - 1) / C::TEAMS;               // block columns a thread owns in the VN phase
-    static constexpr int ROWS = C::GROUPS;
-    static constexpr int CH_COL = ROWS * TmemMsgs::ROW_COLS;                  // first channel column of a thread's stack
-    static constexpr int STACK = CH_COL + 32;                                 // TMEM columns per thread
+    static constexpr int STACK = 32;                                          // TMEM columns per thread: its channel values
     static constexpr int NEED = (WARPS + 3) / 4 * STACK;
     static constexpr int COLS = NEED <= 32 ? 32 : NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
     static constexpr int MAX_CTAS = 512 / COLS;
@@ -85,6 +86,16 @@ template <class C, int T> struct TeamBase { static constexpr int value = TeamBas
 template <class C> struct TeamBase<C, 0> { static constexpr int value = 0; };
 
 // ---- CN phase: the rows of a team back to back, software pipelined (front of row g+1 next to back of row g) ----
+// A row's messages of the PREVIOUS pass: the edge buffer still holds them (the variable-node phase only reads it), and the
+// words are the thread's own -- one LDS.64 per edge at an immediate offset, no tensor-memory round trip, no store.
+template <int Z, class... S>
+__device__ __forceinline__ void row_prev(Row<S...>, RowMsg<sizeof...(S)>& m, const float2* __restrict__ ebuf, const int r, const int slot0)
+{
+    constexpr int D = sizeof...(S);
+#pragma unroll
+    for (int k = 0; k < D; ++k) m.v[k] = ebuf[(slot0 + k) * Z + r];
+}
+
 template <int Z, class... S>
 __device__ __forceinline__ void row_emit(Row<S...>, const RowMsg<sizeof...(S)>& m, float2* __restrict__ ebuf, const int r,
                                          const int slot0, const bool act)
@@ -98,49 +109,45 @@ __device__ __forceinline__ void row_emit(Row<S...>, const RowMsg<sizeof...(S)>& 
 #endif
 }
 
-template <int Z, int TEAM, int TBASE, int EOFF, int ROW, bool EARLY, class GCUR>
-__device__ __forceinline__ void cn_pipe(TmemMsgs& ms, const float2* __restrict__ post, float2* __restrict__ ebuf, const int r,
-                                        const bool fix_odd, const bool act, const bool first_pass, bool& ua, bool& ub,
+template <int Z, int TEAM, int TBASE, int EOFF, bool EARLY, class GCUR>
+__device__ __forceinline__ void cn_pipe(const float2* __restrict__ post, float2* __restrict__ ebuf, const int r,
+                                        const bool fix_odd, const bool act, bool& ua, bool& ub,
                                         RowMsg<TeamRow<TEAM, GCUR>::type::D>& mcur,
                                         const RowFront2<TeamRow<TEAM, GCUR>::type::D>& fcur, GCUR)
 {
     using R = typename TeamRow<TEAM, GCUR>::type;
     row_back2(R(), mcur, fcur);
     row_emit<Z>(R(), mcur, ebuf, r, TBASE + EOFF, act);
-    if constexpr (R::D > 0) ms.template store<EOFF, ROW>(mcur);
 }
 
-template <int Z, int TEAM, int TBASE, int EOFF, int ROW, bool EARLY, class GCUR, class GNEXT, class... Rest>
-__device__ __forceinline__ void cn_pipe(TmemMsgs& ms, const float2* __restrict__ post, float2* __restrict__ ebuf, const int r,
-                                        const bool fix_odd, const bool act, const bool first_pass, bool& ua, bool& ub,
+template <int Z, int TEAM, int TBASE, int EOFF, bool EARLY, class GCUR, class GNEXT, class... Rest>
+__device__ __forceinline__ void cn_pipe(const float2* __restrict__ post, float2* __restrict__ ebuf, const int r,
+                                        const bool fix_odd, const bool act, bool& ua, bool& ub,
                                         RowMsg<TeamRow<TEAM, GCUR>::type::D>& mcur,
                                         const RowFront2<TeamRow<TEAM, GCUR>::type::D>& fcur, GCUR, GNEXT gn, Rest... rest)
 {
     using R = typename TeamRow<TEAM, GCUR>::type;
     using RN = typename TeamRow<TEAM, GNEXT>::type;
-    constexpr int NROW = ROW + (R::D > 0 ? 1 : 0);
     RowMsg<RN::D> mnext;
-    if constexpr (RN::D > 0) ms.template load<EOFF + R::D, NROW>(mnext, first_pass);
+    row_prev<Z>(RN(), mnext, ebuf, r, TBASE + EOFF + R::D);
     RowFront2<RN::D> fnext;
     row_front2<Z, EARLY>(RN(), mnext, post, r, 0, fix_odd, act, ua, ub, fnext);
     row_back2(R(), mcur, fcur);
     row_emit<Z>(R(), mcur, ebuf, r, TBASE + EOFF, act);
-    if constexpr (R::D > 0) ms.template store<EOFF, ROW>(mcur);
-    cn_pipe<Z, TEAM, TBASE, EOFF + R::D, NROW, EARLY>(ms, post, ebuf, r, fix_odd, act, first_pass, ua, ub, mnext, fnext, gn, rest...);
+    cn_pipe<Z, TEAM, TBASE, EOFF + R::D, EARLY>(post, ebuf, r, fix_odd, act, ua, ub, mnext, fnext, gn, rest...);
 }
 
 template <int Z, int TEAM, int TBASE, bool EARLY, class G0, class... Rest>
-__device__ __forceinline__ void cn_phase(TmemMsgs& ms, const float2* __restrict__ post, float2* __restrict__ ebuf, const int r,
-                                         const bool fix_odd, const bool act, const bool first_pass, bool& ua, bool& ub,
+__device__ __forceinline__ void cn_phase(const float2* __restrict__ post, float2* __restrict__ ebuf, const int r,
+                                         const bool fix_odd, const bool act, bool& ua, bool& ub,
                                          G0 g0, Rest... rest)
 {
     using R0 = typename TeamRow<TEAM, G0>::type;
     RowMsg<R0::D> m0;
-    ms.begin_pass();
-    if constexpr (R0::D > 0) ms.template load<0, 0>(m0, first_pass);
+    row_prev<Z>(R0(), m0, ebuf, r, TBASE);
     RowFront2<R0::D> f0;
     row_front2<Z, EARLY>(R0(), m0, post, r, 0, fix_odd, act, ua, ub, f0);
-    cn_pipe<Z, TEAM, TBASE, 0, 0, EARLY>(ms, post, ebuf, r, fix_odd, act, first_pass, ua, ub, m0, f0, g0, rest...);
+    cn_pipe<Z, TEAM, TBASE, 0, EARLY>(post, ebuf, r, fix_odd, act, ua, ub, m0, f0, g0, rest...);
 }
 
 // ---- VN phase: posterior of column t of block column CB = channel value + its messages in schedule order ----
@@ -236,12 +243,8 @@ __device__ __forceinline__ void decode_gather(Code<Z, N, G...>, const float* __r
     const uint32_t stage = (uint32_t)__cvta_generic_to_shared(stage_f);
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    TmemMsgs ms;
-    {
-        const uint32_t warp = threadIdx.x >> 5;
-        ms.taddr0 = s_tmem + (((warp & 3u) * 32u) << 16) + (warp >> 2) * (uint32_t)SH::STACK;
-    }
-    const uint32_t ch_addr = ms.taddr0 + SH::CH_COL;
+    // a thread owns the TMEM lane of its warp quarter (.32x32b: lane i of the warp <-> TMEM lane 32 * (warp % 4) + i)
+    const uint32_t ch_addr = s_tmem + ((((threadIdx.x >> 5) & 3u) * 32u) << 16) + (threadIdx.x >> 7) * (uint32_t)SH::STACK;
 
     ChannelConst cc;
     cc.noise_dev = mc.noise_dev; cc.llr_scale = mc.llr_scale; cc.amp = mc.amp;
@@ -321,7 +324,12 @@ __device__ __forceinline__ void decode_gather(Code<Z, N, G...>, const float* __r
             }
             tmem_wait_st();
             tmem_st32(ch_addr, chv);
-            ms.template begin_frame_rows<SH::ROWS>();
+            if (row_ok) {                                // the messages of "pass -1" are zero
+                const int tb = team == 0 ? TeamBase<C, 0>::value : team == 1 ? TeamBase<C, 1>::value : team == 2 ? TeamBase<C, 2>::value : TeamBase<C, 3>::value;
+                const int ts = team == 0 ? C::template TeamSlots<0>::value : team == 1 ? C::template TeamSlots<1>::value
+                             : team == 2 ? C::template TeamSlots<2>::value : C::template TeamSlots<3>::value;
+                for (int s = 0; s < ts; ++s) ebuf[(tb + s) * Z + r] = f2(0.f, 0.f);
+            }
         }
         __syncthreads();                                 // posterior complete, stage consumed -> prefetch the next pair
         if (use_tma && threadIdx.x == 0 && p_next < pairs)
@@ -331,11 +339,10 @@ __device__ __forceinline__ void decode_gather(Code<Z, N, G...>, const float* __r
         bool done_a = false, done_b = !has_b;
         for (int it = 0; it < max_iter; ++it) {
             bool ua = false, ub = false;
-            const bool first = it == 0;
-            if (team == 0) cn_phase<Z, 0, TeamBase<C, 0>::value, EARLY>(ms, post, ebuf, r, fix_odd != 0, row_ok, first, ua, ub, G()...);
-            if constexpr (C::TEAMS > 1) { if (team == 1) cn_phase<Z, 1, TeamBase<C, 1>::value, EARLY>(ms, post, ebuf, r, fix_odd != 0, row_ok, first, ua, ub, G()...); }
-            if constexpr (C::TEAMS > 2) { if (team == 2) cn_phase<Z, 2, TeamBase<C, 2>::value, EARLY>(ms, post, ebuf, r, fix_odd != 0, row_ok, first, ua, ub, G()...); }
-            if constexpr (C::TEAMS > 3) { if (team == 3) cn_phase<Z, 3, TeamBase<C, 3>::value, EARLY>(ms, post, ebuf, r, fix_odd != 0, row_ok, first, ua, ub, G()...); }
+            if (team == 0) cn_phase<Z, 0, TeamBase<C, 0>::value, EARLY>(post, ebuf, r, fix_odd != 0, row_ok, ua, ub, G()...);
+            if constexpr (C::TEAMS > 1) { if (team == 1) cn_phase<Z, 1, TeamBase<C, 1>::value, EARLY>(post, ebuf, r, fix_odd != 0, row_ok, ua, ub, G()...); }
+            if constexpr (C::TEAMS > 2) { if (team == 2) cn_phase<Z, 2, TeamBase<C, 2>::value, EARLY>(post, ebuf, r, fix_odd != 0, row_ok, ua, ub, G()...); }
+            if constexpr (C::TEAMS > 3) { if (team == 3) cn_phase<Z, 3, TeamBase<C, 3>::value, EARLY>(post, ebuf, r, fix_odd != 0, row_ok, ua, ub, G()...); }
             if (!row_ok) ua = ub = false;
             if (EARLY && it > 0) {
                 // the posterior of pass it-1 is still in place (the VN phase of this pass has not run): a frame whose
