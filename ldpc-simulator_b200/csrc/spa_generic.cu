@@ -32,6 +32,7 @@
 // The kernels are HBM-streaming by construction (per pass and frame: read E,
 // write E, read E, plus O(n) vectors); DESIGN.md gives the roofline.
 #include "ldpc_common.cuh"
+#include "f64_math.cuh"
 
 namespace ldpc {
 
@@ -45,8 +46,15 @@ template <> struct Num<double> {
     static __device__ __forceinline__ double tanh_arg_limit() { return 17.5; }
     static __device__ __forceinline__ double unit_clip() { return 0.99999999999999878; }
     static __device__ __forceinline__ double small_tanh() { return 1e-10; }
+    // f64_math.cuh: tanh / atanh / division restricted to the arguments the check node can produce (3.3 x fewer
+    // instructions than libm's; <= 3.5 ulp, correctly rounded tanh near saturation).  -DLDPC_F64_LIBM: CUDA's libm.
+#ifdef LDPC_F64_LIBM
     static __device__ __forceinline__ double tanh_(double x) { return tanh(x); }
     static __device__ __forceinline__ double atanh_(double x) { return atanh(x); }
+#else
+    static __device__ __forceinline__ double tanh_(double x) { return f64::tanh_half(x + x); }
+    static __device__ __forceinline__ double atanh_(double x) { return 0.5 * f64::two_atanh(x); }
+#endif
     static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
 };
 template <> struct Num<float> {
@@ -110,6 +118,9 @@ template <bool FAST, typename T>
 __device__ __forceinline__ T quotient(T total, T tq)
 {
     if constexpr (FAST) return total * mufu_rcp(tq);
+#ifndef LDPC_F64_LIBM
+    else if constexpr (sizeof(T) == 8) return f64::divide(total, tq);
+#endif
     else return total / tq;
 }
 
