@@ -68,9 +68,12 @@ template <> struct Num<float> {
     static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
 };
 
-template <typename T>
+template <typename T, bool TAB = true>
 __device__ __forceinline__ T tanh_half_clipped(T msg)
 {
+#ifndef LDPC_F64_LIBM
+    if constexpr (sizeof(T) == 8) return f64::tanh_half<TAB>(msg);    // clip included
+#endif
     const T h = msg / T(2);
     if (h > Num<T>::tanh_arg_limit()) return Num<T>::unit_clip();
     if (h < -Num<T>::tanh_arg_limit()) return -Num<T>::unit_clip();
@@ -102,7 +105,8 @@ __device__ __forceinline__ float mufu_ex2(float v) { float y; asm("ex2.approx.ft
 __device__ __forceinline__ float mufu_lg2(float v) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v)); return y; }
 __device__ __forceinline__ float mufu_rcp(float v) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v)); return y; }
 
-template <bool FAST, typename T>
+// TAB: fp64 coefficients from constant memory (unrolled rows) or as literals (rolled loops), see f64_math.cuh
+template <bool FAST, typename T, bool TAB = true>
 __device__ __forceinline__ T tanh_half(T msg)
 {
     if constexpr (FAST) {
@@ -110,7 +114,7 @@ __device__ __forceinline__ T tanh_half(T msg)
         const float t = fminf((1.0f - x) * mufu_rcp(1.0f + x), Num<float>::unit_clip());
         return copysignf(t, msg);
     } else {
-        return tanh_half_clipped<T>(msg);
+        return tanh_half_clipped<T, TAB>(msg);
     }
 }
 
@@ -133,6 +137,15 @@ __device__ __forceinline__ T two_atanh(T r)          // r already clipped to +-u
     } else {
         return T(2) * Num<T>::atanh_(r);
     }
+}
+
+template <bool FAST, typename T, bool TAB = true>
+__device__ __forceinline__ T clipped_two_atanh(T r)  // E = 2 atanh(clip(r)), :167-168
+{
+#ifndef LDPC_F64_LIBM
+    if constexpr (!FAST && sizeof(T) == 8) return f64::two_atanh<TAB>(r);      // clip included
+#endif
+    return two_atanh<FAST, T>(clip_unit<T>(r));
 }
 
 // Per-chunk bookkeeping living in the workspace.
@@ -269,7 +282,7 @@ k_check_nodes(int m, const int32_t* __restrict__ row_ptr, const int32_t* __restr
                         for (int u = 0; u < MAXD; ++u)
                             if (u < d && u != q) r *= tv[u];
                     }
-                    T e = two_atanh<FAST, T>(clip_unit<T>(r));
+                    T e = clipped_two_atanh<FAST, T>(r);
                     if (fix_odd && (d & 1)) e = -e;
                     E[(size_t)(a + q) * Fc + f] = e;
                 }
@@ -278,7 +291,7 @@ k_check_nodes(int m, const int32_t* __restrict__ row_ptr, const int32_t* __restr
             // first sweep: park tanh(M/2) in this pass' message slot (E is double buffered, so the
             // previous messages stay intact); second sweep: read it back, divide, atanh, overwrite.
             for (int q = 0; q < d; ++q) {
-                const T tq = tanh_half<FAST, T>(v2c_message<T>(lch, post, Eold, col_idx[a + q], a + q, Fc, f, first_pass));
+                const T tq = tanh_half<FAST, T, false>(v2c_message<T>(lch, post, Eold, col_idx[a + q], a + q, Fc, f, first_pass));
                 E[(size_t)(a + q) * Fc + f] = tq;
                 total *= tq;
             }
@@ -291,10 +304,10 @@ k_check_nodes(int m, const int32_t* __restrict__ row_ptr, const int32_t* __restr
                     r = T(1);
                     for (int u = 0; u < d; ++u) {
                         if (u == q) continue;
-                        r *= tanh_half<FAST, T>(v2c_message<T>(lch, post, Eold, col_idx[a + u], a + u, Fc, f, first_pass));
+                        r *= tanh_half<FAST, T, false>(v2c_message<T>(lch, post, Eold, col_idx[a + u], a + u, Fc, f, first_pass));
                     }
                 }
-                T e = two_atanh<FAST, T>(clip_unit<T>(r));
+                T e = clipped_two_atanh<FAST, T, false>(r);
                 if (fix_odd && (d & 1)) e = -e;
                 E[(size_t)(a + q) * Fc + f] = e;
             }
@@ -331,7 +344,7 @@ k_check_rows_small(int m, const int32_t* __restrict__ row_ptr, const int32_t* __
         const int a = row_ptr[i], d = row_ptr[i + 1] - a;
         if (d == 0) continue;
         for (int q = lane; q < d; q += 32)
-            tv[q] = tanh_half<FAST, T>(v2c_message<T>(lch, post, Eold, col_idx[a + q], a + q, Fc, f, first_pass));
+            tv[q] = tanh_half<FAST, T, false>(v2c_message<T>(lch, post, Eold, col_idx[a + q], a + q, Fc, f, first_pass));
         __syncwarp();
         T total = T(1);
         for (int q = 0; q < d; ++q) total *= tv[q];             // every lane: same order, same value
@@ -345,7 +358,7 @@ k_check_rows_small(int m, const int32_t* __restrict__ row_ptr, const int32_t* __
                 for (int u = 0; u < d; ++u)
                     if (u != q) r *= tv[u];
             }
-            T e = two_atanh<FAST, T>(clip_unit<T>(r));
+            T e = clipped_two_atanh<FAST, T, false>(r);
             if (fix_odd && (d & 1)) e = -e;
             E[(size_t)(a + q) * Fc + f] = e;
         }
