@@ -517,7 +517,9 @@ def main():
     _native.check(_native.lib().ldpc_measure_mufu_peak(C.byref(pk), None))
     mufu_peak = pk.value
     alg_transc = 2.0 * edges * MAX_ITER * F                 # one tanh + one atanh per edge and pass
-    issued_mufu = 3.0 * edges * MAX_ITER * F                # what the kernel issues: ex2 + 2 x lg2
+    # what the kernel issues per edge and pass: ex2 + lg2 + one reciprocal per two edges (an odd row's last edge has its own):
+    # 192 MUFU per pass and frame for the 76 circulants of this base matrix (profiles/r2_sass_gather_wimax2304.txt)
+    issued_mufu = (192.0 / 76.0) * edges * MAX_ITER * F
     sfu_achieved = alg_transc / (kernel_ms * 1e-3)
     peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
     hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
@@ -543,23 +545,27 @@ def main():
         else:
             traffic_src = "kernel sources changed since the ncu capture %s: not quoted" % cap.get("file")
     sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
-    # shared memory, algorithmic bytes per edge, pass and frame: posterior read 4 + message to the edge buffer 4 +
-    # message read by the variable node 4 + posterior write 4 n/E
-    smem_bytes = (12.0 + 4.0 * n / edges) * edges * MAX_ITER * F
+    # shared memory, algorithmic bytes per edge, pass and frame: posterior read 4 + previous message read 4 + message to
+    # the edge buffer 4 + message read by the variable node 4 + posterior write 4 n/E
+    smem_bytes = (16.0 + 4.0 * n / edges) * edges * MAX_ITER * F
     smem_peak = 128.0 * torch.cuda.get_device_properties(dev).multi_processor_count * sm_hz
     roofline = {
         "bound": "sfu", "achieved": sfu_achieved / 1e9, "peak": mufu_peak / 1e9, "unit": "Gop/s",
         "frac": sfu_achieved / mufu_peak, "traffic": traffic, "traffic_source": traffic_src,
-        "note": "resident kernel (two frames per thread, messages in tensor memory): messages never leave the SM, HBM is "
-                "not the bound; achieved = 2 algorithmic transcendentals per edge and pass / kernel time (CUDA events); "
-                "peak = MUFU ex2 ops/s measured in this run by ldpc_measure_mufu_peak; the kernel issues 3 MUFU per edge "
-                "and pass, so pipe utilisation = 1.5 x frac",
+        "note": "resident kernel (two frames per thread, messages in shared memory / registers): messages never leave the "
+                "SM, HBM is not the bound; achieved = 2 algorithmic transcendentals per edge and pass / kernel time (CUDA "
+                "events); peak = MUFU ex2 ops/s measured in this run by ldpc_measure_mufu_peak; the kernel issues 2.53 MUFU "
+                "per edge and pass (ex2, lg2, one rcp per two edges), so pipe utilisation = 1.26 x frac.  The instruction "
+                "mix itself (not the MUFU pipe) is the floor: its exact opcode mix runs at 51 cycles per edge and frame pair "
+                "= 11.5 Gbit/s in isolation (tools/pipe_probe5.cu, profiles/r2_pipe_probe5.txt)",
         "mufu_pipe_utilisation": issued_mufu / (kernel_ms * 1e-3) / mufu_peak,
         "kernel_ms": kernel_ms,
         "smem": {"bound": "smem", "achieved": smem_bytes / (kernel_ms * 1e-3) / 1e9, "peak": smem_peak / 1e9, "unit": "GB/s",
                  "frac": smem_bytes / (kernel_ms * 1e-3) / smem_peak,
-                 "note": "algorithmic shared-memory bytes (12 + 4 n/E per edge, pass and frame) against 128 B/clk/SM at the "
-                         "sampled SM clock; ncu LSU wavefront share of the same kernel: profiles/"},
+                 "note": "algorithmic shared-memory bytes (16 + 4 n/E per edge, pass and frame: posterior read, previous "
+                         "message read, message write, message read by the variable node, posterior write) against 128 "
+                         "B/clk/SM at the sampled SM clock; ncu LSU wavefront share of the same kernel: "
+                         "profiles/r2_ncu_gather_summary.txt"},
         "hbm": {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
     }

@@ -381,8 +381,12 @@ extern "C" int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t fr
     const int words = (n + 31) / 32;
     const bool resident = use_resident(g, dtype, flags) && !norm_llr_host;
     const bool need_z_dev = z_host || !resident;       // generic kernels always produce bytes
-    // chunk size: ~64 MB of LLRs per slot for the resident path, bounded workspace for the generic one
-    int64_t chunk = std::max<int64_t>(32, ((int64_t)64 << 20) / (int64_t)(n * esz));
+    // chunk size: ~24 MB of LLRs per slot for the resident path, bounded workspace for the generic one
+    // (measured, profiles/r2_tuning.md: 64 MB chunks leave the first copy and the last kernel of a call exposed --
+    // 6.32 Gbit/s end to end; 32 MB 6.49; 16 MB 6.43; below that the per-chunk launches cost more than they hide)
+    int64_t chunk_mb = 24;
+    if (const char* e = getenv("LDPC_HOST_CHUNK_MB")) chunk_mb = std::max(1, atoi(e));      // tuning experiments only
+    int64_t chunk = std::max<int64_t>(32, (chunk_mb << 20) / (int64_t)(n * esz));
     if (!resident) {
         const size_t per32 = generic_workspace_bytes(g, 32, dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32);
         const int64_t by_ws = std::max<int64_t>(32, (int64_t)(((size_t)3 << 30) / per32) * 32);
@@ -443,11 +447,24 @@ extern "C" int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t fr
         return LDPC_OK;
     };
 
+    // The first copy of a call and its last kernel + read-back overlap with nothing: the resident path starts and
+    // ends with quarter and half chunks (whole waves), so that less of the call runs un-overlapped.
+    const int64_t wave = 4 * (int64_t)di.sm_count;
+    const bool ramp = resident && chunk >= 8 * wave && frames >= 6 * chunk;
+    auto part = [&](int64_t q) { return std::max(wave, chunk / q / wave * wave); };
     int s = 0;
-    for (int64_t f0 = 0; f0 < frames; f0 += chunk, s = (s + 1) % nslots) {
+    int64_t c = 0, step_no = 0;
+    for (int64_t f0 = 0; f0 < frames; f0 += c, s = (s + 1) % nslots, ++step_no) {
         if ((rc = drain(s))) return rc;
         HostSlot& sl = g_pipe.slot[s];
-        const int64_t c = std::min<int64_t>(chunk, frames - f0);
+        const int64_t left = frames - f0;
+        c = std::min<int64_t>(chunk, left);
+        if (ramp) {
+            if (step_no == 0) c = part(4);
+            else if (step_no == 1) c = part(2);
+            else if (left <= part(4) + part(2) + chunk && left > part(4) + part(2)) c = left - part(4) - part(2);   // last full-size piece
+            else if (left <= part(4) + part(2) && left > part(4)) c = left - part(4);
+        }
         const char* src = (const char*)llr_host + (size_t)f0 * n * esz_in;
         const size_t in_bytes = (size_t)c * n * esz_in;
         if (!in_pinned) { staging_copy(sl.h_in, src, in_bytes); src = (const char*)sl.h_in; }

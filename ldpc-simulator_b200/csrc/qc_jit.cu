@@ -36,7 +36,8 @@ namespace {
 struct Schedule {
     int teams = 1;
     int max_slot = 0;                       // most messages a thread keeps in registers
-    int min_deg = 0;
+    int min_deg = 0, max_deg = 0;
+    int edges = 0;                          // circulants of the base matrix
     std::vector<std::vector<int>> groups;   // rows of each group by team, -1 = none
     std::vector<char> first;                // [mb*nb] first row (in schedule order) touching the column block
 };
@@ -108,6 +109,8 @@ Schedule schedule_rows(const QcInfo& qc)
     }
     s.max_slot = *std::max_element(load.begin(), load.end());
     s.min_deg = *std::min_element(deg.begin(), deg.end());
+    s.max_deg = *std::max_element(deg.begin(), deg.end());
+    for (int d : deg) s.edges += d;
     return s;
 }
 
@@ -139,14 +142,49 @@ std::string code_type_text(const QcInfo& qc, const Schedule& s)
     return t + ">";
 }
 
-std::string jit_source(const std::string& code_type)
+// Host-side twin of qc::GatherShape (qc_kernel_gather.cuh): does the two-frames-per-thread gather kernel exist for this
+// base matrix, and with which launch shape.
+struct GatherHost {
+    bool fits = false;
+    int threads = 0, cols = 32, max_ctas = 1, minb = 1;
+    size_t smem = 0;
+};
+
+// NVRTC's front end computes shared-memory addresses in 64 bits (nvcc's uses 32-bit pointers for the shared window):
+// the run-time compiled gather kernel carries 0.2 address instructions per edge more than the nvcc build, its pass body
+// (38 KB) no longer fits the instruction cache, and it is SLOWER than the one-frame kernel of the same module
+// (profiles/r2_tuning.md: z = 92: 6.57 against 7.37 Gbit/s; the nvcc build of the same source: 2000 instead of 2428
+// instructions per pass).  It is therefore opt-in (LDPC_JIT_GATHER=1) until its shared-memory accesses are spelled with
+// explicit 32-bit window addresses; results are bit-identical either way (tests/test_gpu_parity.py).
+bool jit_gather_enabled()
 {
-    return std::string("#include \"qc_kernel.cuh\"\n"
-                       "namespace ldpc { namespace qc {\n"
-                       "using JitCode = ") + code_type + ";\n"
-           "using JitShape = LaunchShape<JitCode>;\n"
-           "} }\n"
-           "#define LDPC_JIT_ARGS const float* __restrict__ llr, ldpc::qc::Outputs out, long long frames, int max_iter, \\\n"
+    const char* e = getenv("LDPC_JIT_GATHER");
+    return e && *e && *e != '0';
+}
+
+GatherHost gather_shape(const QcInfo& qc, const Schedule& s)
+{
+    GatherHost h;
+    const int tz = (qc.z + 31) / 32 * 32;
+    h.threads = tz * s.teams;
+    const int warps = h.threads / 32;
+    const int own = (qc.nb + s.teams - 1) / s.teams;
+    const int need = (warps + 3) / 4 * 32;
+    h.cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+    h.max_ctas = 512 / h.cols;
+    h.smem = sizeof(float) * 2 * ((size_t)qc.z * qc.nb * 2 + (size_t)s.edges * qc.z);
+    const int b0 = 65536 / (h.threads * 168);
+    h.minb = std::min(std::max(b0, 1), h.max_ctas);
+    h.fits = need <= 512 && s.max_deg <= 8 && 2 * own <= 32 && h.threads <= 1024 && h.smem + 2048 <= 227 * 1024 &&
+             jit_gather_enabled();
+    return h;
+}
+
+std::string jit_source(const std::string& code_type, bool with_gather)
+{
+    std::string src = with_gather ? "#include \"qc_kernel_gather.cuh\"\n" : "#include \"qc_kernel.cuh\"\n";
+    src += "namespace ldpc { namespace qc {\nusing JitCode = " + code_type + ";\nusing JitShape = LaunchShape<JitCode>;\n} }\n";
+    src += "#define LDPC_JIT_ARGS const float* __restrict__ llr, ldpc::qc::Outputs out, long long frames, int max_iter, \\\n"
            "    int fix_odd, ldpc::McParams mc, unsigned long long* __restrict__ work_counter\n"
            "extern \"C\" __global__ void __launch_bounds__(ldpc::qc::JitShape::THREADS, ldpc::qc::JitShape::MINB)\n"
            "ldpc_jit_fixed(LDPC_JIT_ARGS)\n"
@@ -154,6 +192,12 @@ std::string jit_source(const std::string& code_type)
            "extern \"C\" __global__ void __launch_bounds__(ldpc::qc::JitShape::THREADS, ldpc::qc::JitShape::MINB)\n"
            "ldpc_jit_early(LDPC_JIT_ARGS)\n"
            "{ ldpc::qc::decode_frames<ldpc::qc::JitShape::THREADS, true>(ldpc::qc::JitCode(), llr, out, frames, max_iter, fix_odd, mc, work_counter); }\n";
+    if (with_gather)      // two frames per thread, gather structure (qc_kernel_gather.cuh), fixed iteration count
+        src += "using JitGather = ldpc::qc::GatherShape<ldpc::qc::JitCode>;\n"
+               "extern \"C\" __global__ void __launch_bounds__(JitGather::THREADS, JitGather::MINB)\n"
+               "ldpc_jit_gather(LDPC_JIT_ARGS)\n"
+               "{ ldpc::qc::decode_gather<JitGather::THREADS, false>(ldpc::qc::JitCode(), llr, out, frames, max_iter, fix_odd, mc, work_counter); }\n";
+    return src;
 }
 
 // ---- NVRTC through dlopen ----------------------------------------------------------------------
@@ -329,6 +373,10 @@ struct JitKernel {
     int per_sm[2] = {0, 0};
     int threads = 0;
     size_t smem = 0;
+    // two frames per thread, gather structure (fixed iterations only), when the code fits it
+    CUfunction gather = nullptr;
+    int gather_per_sm = 0, gather_threads = 0;
+    size_t gather_smem = 0;
 };
 
 std::mutex g_jit_mu;
@@ -357,7 +405,8 @@ std::shared_ptr<JitKernel> build_kernel(const ldpc_graph* g)
     auto k = std::make_shared<JitKernel>();
     const Schedule s = schedule_rows(g->qc);
     std::string cubin;
-    if (compile_cubin(jit_source(code_type_text(g->qc, s)), &cubin) != LDPC_OK) { k->error = ldpc_last_error(); return k; }
+    const GatherHost gh = gather_shape(g->qc, s);
+    if (compile_cubin(jit_source(code_type_text(g->qc, s), gh.fits), &cubin) != LDPC_OK) { k->error = ldpc_last_error(); return k; }
     const Driver& drv = driver();
     if (!drv.ok) { k->error = "CUDA driver entry points unavailable"; return k; }
     k->threads = (g->qc.z + 31) / 32 * 32 * s.teams;
@@ -370,6 +419,26 @@ std::shared_ptr<JitKernel> build_kernel(const ldpc_graph* g)
         LDPC_DRV_TRY(k, drv.funcSetAttribute(k->fn[i], CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100));
         LDPC_DRV_TRY(k, drv.occupancy(&k->per_sm[i], k->fn[i], k->threads, k->smem));
         if (k->per_sm[i] < 1) { k->error = "run-time specialised kernel does not fit on an SM"; return k; }
+    }
+    if (gh.fits) {
+        DeviceInfo di;
+        if (get_device_info(&di) != LDPC_OK) { k->error = ldpc_last_error(); return k; }
+        // at most max_ctas CTAs may share an SM (tensor-memory columns): ask for more than 1/(max_ctas+1) of its shared
+        // memory, as the static launcher does (spa_qc_spec.cu: launch_gather)
+        k->gather_smem = std::max(gh.smem, (size_t)di.max_smem_optin / (gh.max_ctas + 1) + 1024);
+        k->gather_threads = gh.threads;
+        if (k->gather_smem <= (size_t)di.max_smem_optin) {
+            LDPC_DRV_TRY(k, drv.moduleGetFunction(&k->gather, k->module, "ldpc_jit_gather"));
+            LDPC_DRV_TRY(k, drv.funcSetAttribute(k->gather, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)k->gather_smem));
+            LDPC_DRV_TRY(k, drv.funcSetAttribute(k->gather, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100));
+            int api = 0;
+            LDPC_DRV_TRY(k, drv.occupancy(&api, k->gather, k->gather_threads, k->gather_smem));
+            // the occupancy query answers for the default carve-out; the kernel is compiled for minb CTAs per SM
+            // (launch bounds), and the whole shared memory of the SM is available to it
+            const int by_smem = (int)((size_t)228 * 1024 / (k->gather_smem + 1024 + 256));
+            k->gather_per_sm = std::min(gh.max_ctas, std::max(api, std::min(gh.minb, by_smem)));
+            if (k->gather_per_sm < 1) k->gather = nullptr;
+        }
     }
     k->ok = true;
     return k;
@@ -435,14 +504,20 @@ int qc_jit_decode(const ldpc_graph* g, int64_t frames, int max_iter, unsigned fl
         counter = (unsigned long long*)ws;
         LDPC_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
     }
-    const int grid = (int)std::min<int64_t>(frames, (int64_t)k->per_sm[early] * di.sm_count);
+    // same choice as the static launcher (spa_qc_spec.cu: launch_code): fixed iteration count and enough frames to fill
+    // the machine with CTAs of two frames -> the gather kernel; early termination or a small batch -> one frame per CTA
+    const bool use_gather = k->gather && !early && !(flags & LDPC_FLAG_ONE_FRAME) && frames >= 4 * (int64_t)di.sm_count;
+    const int grid = use_gather ? (int)std::min<int64_t>((frames + 1) / 2, (int64_t)k->gather_per_sm * di.sm_count)
+                                : (int)std::min<int64_t>(frames, (int64_t)k->per_sm[early] * di.sm_count);
     qc::Outputs out{z_dev, zbits_dev, conv_dev, ok_dev, post_dev};
     long long nframes = frames;
     int fix_odd = (flags & LDPC_FLAG_FIX_ODD_SIGN) ? 1 : 0;
     McParams mc = mc_in;
     void* args[] = {&llr_dev, &out, &nframes, &max_iter, &fix_odd, &mc, &counter};
     const Driver& drv = driver();
-    CUresult r = drv.launchKernel(k->fn[early], grid, 1, 1, k->threads, 1, 1, (unsigned)k->smem, (CUstream)stream, args, nullptr);
+    CUresult r = use_gather
+        ? drv.launchKernel(k->gather, grid, 1, 1, k->gather_threads, 1, 1, (unsigned)k->gather_smem, (CUstream)stream, args, nullptr)
+        : drv.launchKernel(k->fn[early], grid, 1, 1, k->threads, 1, 1, (unsigned)k->smem, (CUstream)stream, args, nullptr);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (r != CUDA_SUCCESS) {
         const char* s = nullptr;
@@ -476,7 +551,7 @@ extern "C" int ldpc_host_jit_compile(int z, int mb, int nb, const int16_t* shift
     if (cubin_bytes) {
         if (const char* why = jit_shape_problem(qc, s)) { set_error("no specialised kernel for this base matrix: %s", why); return LDPC_ERR_UNSUPPORTED; }
         std::string cubin;
-        int rc = compile_cubin(jit_source(text), &cubin);
+        int rc = compile_cubin(jit_source(text, gather_shape(qc, s).fits), &cubin);
         if (rc) return rc;
         *cubin_bytes = cubin.size();
     }

@@ -583,6 +583,35 @@ def test_pair_kernel_is_bit_identical_to_the_one_frame_kernel(name, frames, earl
         assert 0.05 < pair.ok.mean() < 1.0        # a mix of converged and failed frames inside the pairs
 
 
+@pytest.mark.parametrize("seed,z,mb,nb,max_deg,frames", [(11, 48, 12, 24, 7, 1500), (12, 27, 6, 13, 8, 1201), (13, 96, 3, 9, 5, 640)])
+def test_run_time_specialised_gather_kernel_is_bit_identical_to_the_one_frame_kernel(seed, z, mb, nb, max_deg, frames, monkeypatch):
+    """With LDPC_JIT_GATHER=1 csrc/qc_jit.cu compiles the two-frames-per-thread gather kernel (qc_kernel_gather.cuh) for
+    base matrices outside the registry as well; a fixed-iteration batch of at least 4 x SMs frames runs it.  Same IEEE
+    operations per frame as the one-frame kernel of the same NVRTC module (LDPC_FLAG_ONE_FRAME): everything must be
+    identical.  (Opt-in: NVRTC's 64-bit shared-memory addressing makes it slower than the one-frame kernel, see qc_jit.cu.)"""
+    import _native
+    monkeypatch.setenv("LDPC_JIT_GATHER", "1")
+    rng = np.random.default_rng(seed)
+    shift, h = _random_qc(rng, z, mb, nb, max_deg)
+
+    class G:
+        n, m, row_ptr, col_idx = h.shape[1], h.shape[0], h.indptr.astype(np.int32), h.indices.astype(np.int32)
+        def csr(self):
+            return h
+    code = G()
+    assert (shift >= 0).sum(axis=1).max() <= 8               # the gather kernel's limit: a row is at most 8 edges
+    dec = make_decoder(code, 15, "f32_fast", fix_odd_check_sign=True)
+    assert dec.graph.prepare("f32_fast") == "qc_jit"
+    llr = awgn_llr(rng, frames, code.n, np.resize(np.array([1.0, 3.0, 5.0]), frames), rate=1.0 - mb / nb).astype(np.float32)
+    before = _native.launches()
+    pair = dec.decode_batch(llr, want_posterior=True, want_bits=True, early_termination=False)
+    assert _native.launches() - before == 1
+    one = make_decoder(code, 15, "f32_fast", fix_odd_check_sign=True, one_frame_kernel=True).decode_batch(
+        llr, want_posterior=True, want_bits=True, early_termination=False)
+    for key in ("ok", "conv_it", "z", "zbits", "post"):
+        assert np.array_equal(getattr(pair, key), getattr(one, key)), key
+
+
 def test_pair_kernel_monte_carlo_counters_equal_the_one_frame_kernel():
     """In-kernel Philox channel + error counters: both kernels must count the same events."""
     import _native
