@@ -151,15 +151,16 @@ struct GatherHost {
 };
 
 // NVRTC's front end computes shared-memory addresses in 64 bits (nvcc's uses 32-bit pointers for the shared window):
-// the run-time compiled gather kernel carries 0.2 address instructions per edge more than the nvcc build, its pass body
-// (38 KB) no longer fits the instruction cache, and it is SLOWER than the one-frame kernel of the same module
-// (profiles/r2_tuning.md: z = 92: 6.57 against 7.37 Gbit/s; the nvcc build of the same source: 2000 instead of 2428
-// instructions per pass).  It is therefore opt-in (LDPC_JIT_GATHER=1) until its shared-memory accesses are spelled with
-// explicit 32-bit window addresses; results are bit-identical either way (tests/test_gpu_parity.py).
+// compiled from the plain source the gather kernel carries 0.2 address instructions per edge more than the nvcc build,
+// its pass body (38 KB) no longer fits the instruction cache, and it is SLOWER than the one-frame kernel of the same
+// module (z = 92: 6.57 against 7.37 Gbit/s).  kJitOptions therefore defines LDPC_SMEM_ASM: the two-frame kernels address
+// the shared window explicitly (qc_kernel.cuh: sh_ld2 / sh_st2), which gives 2004 instead of 2428 instructions per pass
+// and 8.41 Gbit/s (z = 48: 7.49 against 5.73-6.36; profiles/r2_jit_gather.jsonl).  LDPC_JIT_GATHER=0 keeps the module to
+// the one-frame kernels (shorter compilation: 4 instead of 17 s per code, once per machine).
 bool jit_gather_enabled()
 {
     const char* e = getenv("LDPC_JIT_GATHER");
-    return e && *e && *e != '0';
+    return !(e && *e == '0');
 }
 
 GatherHost gather_shape(const QcInfo& qc, const Schedule& s)
@@ -293,7 +294,7 @@ void write_file_atomic(const std::string& dir, const std::string& path, const st
     if (ok) rename(tmp.c_str(), path.c_str()); else unlink(tmp.c_str());
 }
 
-const char* const kJitOptions[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+const char* const kJitOptions[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DLDPC_SMEM_ASM"};
 
 // source -> cubin (through the disk cache).  Host only: works without a GPU.
 int compile_cubin(const std::string& src, std::string* cubin)

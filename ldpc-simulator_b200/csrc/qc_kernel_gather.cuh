@@ -93,7 +93,7 @@ __device__ __forceinline__ void row_prev(Row<S...>, RowMsg<sizeof...(S)>& m, con
 {
     constexpr int D = sizeof...(S);
 #pragma unroll
-    for (int k = 0; k < D; ++k) m.v[k] = ebuf[(slot0 + k) * Z + r];
+    for (int k = 0; k < D; ++k) m.v[k] = sh_ld2(ebuf, (slot0 + k) * Z + r);
 }
 
 template <int Z, class... S>
@@ -105,7 +105,7 @@ __device__ __forceinline__ void row_emit(Row<S...>, const RowMsg<sizeof...(S)>& 
     if (!act) return;
 #ifndef LDPC_EXP_NOSMEM
 #pragma unroll
-    for (int k = 0; k < D; ++k) ebuf[(slot0 + k) * Z + r] = m.v[k];
+    for (int k = 0; k < D; ++k) sh_st2(ebuf, (slot0 + k) * Z + r, m.v[k]);
 #endif
 }
 
@@ -164,7 +164,7 @@ __device__ __forceinline__ void gather_row(Row<S...>, float2& acc, const float2*
         if (COLB[k] == CB) {                                     // resolved at compile time
             int idx = t + (Z - SH[k]);                           // check row that owns this column: (t - shift) mod z
             idx = (int)min((unsigned)idx, (unsigned)(idx - Z));
-            acc = f2add(acc, ebuf[(slot0 + k) * Z + idx]);
+            acc = f2add(acc, sh_ld2(ebuf, (slot0 + k) * Z + idx));
         }
     }
 }
@@ -195,7 +195,7 @@ __device__ __forceinline__ void vn_columns(const uint32_t (&ch)[32], float2* __r
     if constexpr (CB < NB) {
         float2 acc = f2(__uint_as_float(ch[2 * K]), __uint_as_float(ch[2 * K + 1]));
         gather_groups<C, CB, 0, 0, 0, 0>(acc, ebuf, t, G()...);
-        post[CB * C::Z + t] = acc;
+        sh_st2(post, CB * C::Z + t, acc);
         vn_columns<C, TEAM, K + 1, G...>(ch, post, ebuf, t);
     }
 }

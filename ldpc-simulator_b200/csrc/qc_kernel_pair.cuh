@@ -29,7 +29,24 @@ namespace qc {
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+// a - b.  In the NVRTC build (LDPC_SMEM_ASM) the negation of __fadd2_rn(a, -b) is not folded into the FADD2 behind the
+// inline-PTX loads (two scalar FADD per edge pair): there it is spelled sub.rn.f32x2, which always is one FADD2.  The nvcc
+// build keeps the intrinsic form: the PTX spelling is 24 instructions per pass shorter but schedules 2 % slower
+// (16.8 -> 17.1 ms, profiles/r2_tuning.md).
+#ifndef LDPC_SMEM_ASM
 __device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, f2neg(b)); }
+#else
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b)
+{
+    unsigned long long ua, ub, ur;
+    float2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(ur) : "l"(ua), "l"(ub));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(ur));
+    return r;
+}
+#endif
 __device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
@@ -167,7 +184,7 @@ __device__ __forceinline__ void row_front2(Row<S...>, RowMsg<sizeof...(S)>& m, c
 #ifdef LDPC_EXP_NOSMEM      // timing experiment (wrong results): no shared-memory traffic in the check-node phase
         const float2 L = f2((float)(idx + c) * 0.01f, (float)(idx - c) * 0.02f);
 #else
-        const float2 L = act ? sm[po + CB[c] + idx] : f2(1.f, 1.f);
+        const float2 L = act ? sh_ld2(sm, po + CB[c] + idx) : f2(1.f, 1.f);
 #endif
         const float2 mu = f2sub(L, m.v[c]);                      // variable->check messages, :260-268
         if (EARLY) { par_a ^= (L.x < 0.f); par_b ^= (L.y < 0.f); }

@@ -584,13 +584,12 @@ def test_pair_kernel_is_bit_identical_to_the_one_frame_kernel(name, frames, earl
 
 
 @pytest.mark.parametrize("seed,z,mb,nb,max_deg,frames", [(11, 48, 12, 24, 7, 1500), (12, 27, 6, 13, 8, 1201), (13, 96, 3, 9, 5, 640)])
-def test_run_time_specialised_gather_kernel_is_bit_identical_to_the_one_frame_kernel(seed, z, mb, nb, max_deg, frames, monkeypatch):
-    """With LDPC_JIT_GATHER=1 csrc/qc_jit.cu compiles the two-frames-per-thread gather kernel (qc_kernel_gather.cuh) for
-    base matrices outside the registry as well; a fixed-iteration batch of at least 4 x SMs frames runs it.  Same IEEE
-    operations per frame as the one-frame kernel of the same NVRTC module (LDPC_FLAG_ONE_FRAME): everything must be
-    identical.  (Opt-in: NVRTC's 64-bit shared-memory addressing makes it slower than the one-frame kernel, see qc_jit.cu.)"""
+def test_run_time_specialised_gather_kernel_is_bit_identical_to_the_one_frame_kernel(seed, z, mb, nb, max_deg, frames):
+    """csrc/qc_jit.cu compiles the two-frames-per-thread gather kernel (qc_kernel_gather.cuh, with explicit 32-bit
+    shared-window addressing under NVRTC) for base matrices outside the registry as well; a fixed-iteration batch of at
+    least 4 x SMs frames runs it.  Same IEEE operations per frame as the one-frame kernel of the same NVRTC module
+    (LDPC_FLAG_ONE_FRAME): everything must be identical."""
     import _native
-    monkeypatch.setenv("LDPC_JIT_GATHER", "1")
     rng = np.random.default_rng(seed)
     shift, h = _random_qc(rng, z, mb, nb, max_deg)
 

@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.join(ROOT, "ldpc-simulator_b200"))
 
 
 def main():
-    os.environ["LDPC_JIT_GATHER"] = "1"      # the run-time compiled gather kernel is opt-in (see csrc/qc_jit.cu)
+
     import torch
     from scipy import sparse
     import _native
