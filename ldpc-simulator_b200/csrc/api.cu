@@ -42,12 +42,6 @@ struct HostSlot {
     bool busy = false;
 };
 constexpr int kSlots = 3;
-struct HostPipe {
-    std::mutex mu;
-    HostSlot slot[kSlots];
-    bool init = false;
-};
-HostPipe g_pipe;
 
 // ---- replay cache for tiny host calls (the per-frame SPA_Decoder.decode) ------------------------
 // A decode of <= 32 frames on the generic kernels is ~4 launches per pass of microsecond kernels: the
@@ -65,8 +59,31 @@ struct ReplayKey {
 };
 struct ReplayEntry { ReplayKey key; cudaGraphExec_t exec = nullptr; uint64_t used = 0; uint64_t launches = 0; };
 constexpr int kReplaySlots = 16;
-ReplayEntry g_replay[kReplaySlots];
-uint64_t g_replay_clock = 0;
+
+// One staging pipeline = three slots (streams, device / pinned buffers) + its replay cache.  ldpc_decode_batch_host takes
+// a FREE pipeline of a small pool, so two decoders driven from two host threads do not serialise on each other (round 1
+// had one process-wide pipeline behind one mutex); only with more concurrent callers than pipelines does a caller wait.
+struct HostPipe {
+    std::mutex mu;
+    HostSlot slot[kSlots];
+    bool init = false;
+    ReplayEntry replay[kReplaySlots];
+    uint64_t replay_clock = 0;
+};
+constexpr int kPipes = 4;
+HostPipe g_pipes[kPipes];
+
+// Lock a pipeline: the first one that is free, else wait for the one this thread hashes to.
+HostPipe& acquire_pipe(std::unique_lock<std::mutex>& lk)
+{
+    for (auto& p : g_pipes) {
+        std::unique_lock<std::mutex> t(p.mu, std::try_to_lock);
+        if (t.owns_lock()) { lk = std::move(t); return p; }
+    }
+    HostPipe& p = g_pipes[std::hash<std::thread::id>()(std::this_thread::get_id()) % kPipes];
+    lk = std::unique_lock<std::mutex>(p.mu);
+    return p;
+}
 
 int grow_dev(void** p, size_t* have, size_t need)
 {
@@ -199,22 +216,22 @@ int decode_device(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, 
     return LDPC_OK;
 }
 
-int init_pipe()
+int init_pipe(HostPipe& pipe)
 {
     for (int s = 0; s < kSlots; ++s) {
-        LDPC_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.slot[s].stream, cudaStreamNonBlocking));
-        LDPC_CUDA_TRY(cudaEventCreateWithFlags(&g_pipe.slot[s].done, cudaEventDisableTiming));
+        LDPC_CUDA_TRY(cudaStreamCreateWithFlags(&pipe.slot[s].stream, cudaStreamNonBlocking));
+        LDPC_CUDA_TRY(cudaEventCreateWithFlags(&pipe.slot[s].done, cudaEventDisableTiming));
     }
-    g_pipe.init = true;
+    pipe.init = true;
     return LDPC_OK;
 }
 
-// <= 32 frames on the generic kernels, caller holds g_pipe.mu.  Outputs are staged in slot 0.
-int decode_host_replay(const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
+// <= 32 frames on the generic kernels, caller holds the pipeline's mutex.  Outputs are staged in slot 0.
+int decode_host_replay(HostPipe& pipe, const ldpc_graph* g, int dtype, int64_t frames, int max_iter, unsigned flags,
                        const void* llr_host, uint8_t* z_host, uint8_t* zbits_host, int32_t* conv_host, uint8_t* ok_host,
                        void* post_host, float* norm_host, int k_info)
 {
-    HostSlot& sl = g_pipe.slot[0];
+    HostSlot& sl = pipe.slot[0];
     const int n = g->n;
     const int gd = dtype == LDPC_F64 ? LDPC_F64 : LDPC_F32;
     const size_t esz = gd == LDPC_F64 ? 8 : 4;
@@ -236,8 +253,8 @@ int decode_host_replay(const ldpc_graph* g, int dtype, int64_t frames, int max_i
     const int outs = (z_host ? 1 : 0) | (zbits_host ? 2 : 0) | (post_host ? 4 : 0) | (norm_host ? 8 : 0);
     const ReplayKey key{g->serial, dtype, frames, max_iter, flags, outs, k_info, sl.d_llr, sl.d_out, sl.d_ws, sl.h_in, sl.h_out};
     ReplayEntry* hit = nullptr;
-    ReplayEntry* victim = &g_replay[0];
-    for (auto& e : g_replay) {
+    ReplayEntry* victim = &pipe.replay[0];
+    for (auto& e : pipe.replay) {
         if (e.exec && e.key == key) { hit = &e; break; }
         if (e.used < victim->used) victim = &e;
     }
@@ -279,7 +296,7 @@ int decode_host_replay(const ldpc_graph* g, int dtype, int64_t frames, int max_i
         victim->launches = g_launches.load(std::memory_order_relaxed) - launches_before;
         hit = victim;
     }
-    hit->used = ++g_replay_clock;
+    hit->used = ++pipe.replay_clock;
     memcpy(sl.h_in, llr_host, in_bytes);
     LDPC_CUDA_TRY(cudaGraphLaunch(hit->exec, sl.stream));
     LDPC_CUDA_TRY(cudaStreamSynchronize(sl.stream));
@@ -410,14 +427,15 @@ extern "C" int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t fr
     const bool out_pinned = is_pinned(z_host) && is_pinned(zbits_host) && is_pinned(conv_iter_host) &&
                             is_pinned(ok_host) && is_pinned(post_host) && is_pinned(norm_llr_host);
 
-    std::lock_guard<std::mutex> lk(g_pipe.mu);
-    if (!g_pipe.init && (rc = init_pipe())) return rc;
+    std::unique_lock<std::mutex> lk;
+    HostPipe& pipe = acquire_pipe(lk);
+    if (!pipe.init && (rc = init_pipe(pipe))) return rc;
     if (!resident && frames <= 32 && !(flags & LDPC_FLAG_NO_REPLAY) && !in_f16)
-        return decode_host_replay(g, dtype, frames, max_iter, flags, llr_host, z_host, zbits_host, conv_iter_host, ok_host,
+        return decode_host_replay(pipe, g, dtype, frames, max_iter, flags, llr_host, z_host, zbits_host, conv_iter_host, ok_host,
                                   post_host, norm_llr_host, k_info);
     const int nslots = (int)std::min<int64_t>(kSlots, (frames + chunk - 1) / chunk);
     for (int s = 0; s < nslots; ++s) {
-        HostSlot& sl = g_pipe.slot[s];
+        HostSlot& sl = pipe.slot[s];
         if ((rc = grow_dev(&sl.d_llr, &sl.d_llr_bytes, (size_t)chunk * n * esz))) return rc;
         if ((rc = grow_dev(&sl.d_out, &sl.d_out_bytes, o_end))) return rc;
         if ((rc = grow_dev(&sl.d_ws, &sl.d_ws_bytes, ws_need))) return rc;
@@ -430,7 +448,7 @@ extern "C" int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t fr
     struct Pending { int64_t f0 = 0, cnt = 0; };
     Pending pend[kSlots];
     auto drain = [&](int s) -> int {      // wait for a slot and copy staged outputs to the caller
-        HostSlot& sl = g_pipe.slot[s];
+        HostSlot& sl = pipe.slot[s];
         if (!sl.busy) return LDPC_OK;
         LDPC_CUDA_TRY(cudaEventSynchronize(sl.done));
         sl.busy = false;
@@ -456,7 +474,7 @@ extern "C" int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t fr
     int64_t c = 0, step_no = 0;
     for (int64_t f0 = 0; f0 < frames; f0 += c, s = (s + 1) % nslots, ++step_no) {
         if ((rc = drain(s))) return rc;
-        HostSlot& sl = g_pipe.slot[s];
+        HostSlot& sl = pipe.slot[s];
         const int64_t left = frames - f0;
         c = std::min<int64_t>(chunk, left);
         if (ramp) {

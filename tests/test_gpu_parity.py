@@ -782,3 +782,29 @@ def test_resident_kernels_are_deterministic_and_identical():
         outs.append(runs[0])
     for o in outs[1:]:
         assert np.array_equal(o.post, outs[0].post) and np.array_equal(o.z, outs[0].z) and np.array_equal(o.conv_it, outs[0].conv_it)
+
+
+def test_two_host_threads_decode_concurrently_on_separate_pipelines():
+    """ldpc_decode_batch_host takes a free staging pipeline of a small pool (csrc/api.cu): two decoders driven from two
+    host threads run side by side and return what they return one after the other."""
+    import threading
+    codes = [load_code("wimax_2304_0.5"), load_code("wimax_576_0.5")]
+    rng = np.random.default_rng(77)
+    llrs = [awgn_llr(rng, 6000, c.n, np.resize(np.array([1.5, 2.5]), 6000)).astype(np.float32) for c in codes]
+    decs = [make_decoder(c, 10, "f32_fast", fix_odd_check_sign=True) for c in codes]
+    want = [d.decode_batch(x, want_posterior=True) for d, x in zip(decs, llrs)]
+    got = [[None] * 4, [None] * 4]
+
+    def work(i):
+        for rep in range(4):
+            got[i][rep] = decs[i].decode_batch(llrs[i], want_posterior=True)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for i in range(2):
+        for rep in range(4):
+            for key in ("z", "ok", "conv_it", "post"):
+                assert np.array_equal(getattr(got[i][rep], key), getattr(want[i], key)), (i, rep, key)
