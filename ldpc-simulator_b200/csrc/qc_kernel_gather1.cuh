@@ -248,8 +248,11 @@ __device__ __forceinline__ void decode_gather1(Code<Z, N, G...>, const float* __
             if constexpr (C::TEAMS > 2) { if (team == 2) cn1_rows<Z, 2, TeamBase<C, 2>::value, 0, 0, EARLY>(taddr0, post, ebuf, r, fix_odd != 0, row_ok, unsat, G()...); }
             if constexpr (C::TEAMS > 3) { if (team == 3) cn1_rows<Z, 3, TeamBase<C, 3>::value, 0, 0, EARLY>(taddr0, post, ebuf, r, fix_odd != 0, row_ok, unsat, G()...); }
             if (!row_ok) unsat = false;
+            bool nearly = it == 0;               // (see decode_frames in qc_kernel.cuh: the eager syndrome test)
             if (EARLY && it > 0) {
-                if (!__syncthreads_or(unsat)) { conv = it - 1; break; }
+                const int open_rows = __syncthreads_count(unsat);
+                if (open_rows == 0) { conv = it - 1; break; }
+                nearly = open_rows <= kEagerSyndromeThreads;
             } else {
                 __syncthreads();
             }
@@ -263,6 +266,18 @@ __device__ __forceinline__ void decode_gather1(Code<Z, N, G...>, const float* __
                 if constexpr (C::TEAMS > 3) { if (team == 3) vn1_columns<C, 3, 0, G...>(ch, post, ebuf, r); }
             }
             __syncthreads();
+            if (EARLY && nearly && it + 1 < max_iter) {
+                // the previous pass left few open checks (or this is the first pass): test this pass' posterior at once
+                // instead of finding out during the next pass
+                bool u = false;
+                if (row_ok) {
+                    if (team == 0) u = team_unsat<Z, 0>(post, r, 0, G()...);
+                    if constexpr (C::TEAMS > 1) { if (team == 1) u = team_unsat<Z, 1>(post, r, 0, G()...); }
+                    if constexpr (C::TEAMS > 2) { if (team == 2) u = team_unsat<Z, 2>(post, r, 0, G()...); }
+                    if constexpr (C::TEAMS > 3) { if (team == 3) u = team_unsat<Z, 3>(post, r, 0, G()...); }
+                }
+                if (!__syncthreads_or(u)) { conv = it; break; }
+            }
         }
         if (conv < 0) {
             bool unsat = false;

@@ -222,7 +222,11 @@ int launch_code(C code, const Args& a)
     // check-node phase + gather (qc_kernel_gather.cuh), 8 % faster than the one-frame kernel.  Early termination: the
     // one-frame kernel, because a pair iterates until BOTH of its frames are done (E[max] of two iteration counts
     // costs more than the pair kernel gains).  The LDPC_FLAG_PAIR_* flags force a variant (tests, A/B timing).
-    if constexpr (qc::Gather1Shape<C>::FITS) if (a.flags & LDPC_FLAG_ONE_GATHER) {
+    // Early termination on a batch that fills the machine: the one-frame GATHER kernel (24 warps per SM) is 4-10 % faster
+    // than the one-frame scatter kernel there (tools/mc_et_probe.py); LDPC_FLAG_ONE_FRAME keeps the latter.
+    const bool et_gather1 = (a.flags & LDPC_FLAG_EARLY_TERM) && a.frames >= 4 * (int64_t)di.sm_count &&
+                            !(a.flags & (LDPC_FLAG_ONE_FRAME | LDPC_FLAG_PAIR_REGS | LDPC_FLAG_PAIR_SCATTER | LDPC_FLAG_PAIR_GATHER));
+    if constexpr (qc::Gather1Shape<C>::FITS) if ((a.flags & LDPC_FLAG_ONE_GATHER) || et_gather1) {
         constexpr int GB = qc::Gather1Shape<C>::MINB;
         return early ? launch_gather1<C, true, T, GB>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream)
                      : launch_gather1<C, false, T, GB>(code, a.g, a.frames, a.max_iter, a.flags, a.llr, a.out, *a.mc, a.ws, a.stream);

@@ -22,8 +22,11 @@ def main():
     from encoder_decoder_data import EncoderDecoderData
     from mc_driver import MonteCarloEngine
 
+    import _native
     name = sys.argv[1] if len(sys.argv) > 1 else "wimax_2304_0.5"
     snrs = [float(a) for a in sys.argv[2:]] or [1.5, 2.0, 2.5, 3.0, 4.0]
+    # LDPC_ET_KERNEL=one_gather | pair_gather: force a kernel variant for the early-termination runs (A/B)
+    variant = {"one_gather": _native.FLAG_ONE_GATHER, "pair_gather": _native.FLAG_PAIR_GATHER}.get(os.environ.get("LDPC_ET_KERNEL", ""), 0)
     code = load_code(name)
     edd = EncoderDecoderData(h=code.sparse_matrix())
     frames = 262144
@@ -31,7 +34,7 @@ def main():
     fixed = MonteCarloEngine(edd, graph="alist", precision="f32_fast", max_iterations=20, early_termination=False,
                              fix_odd_check_sign=True, seed=5)
     et = MonteCarloEngine(edd, graph="alist", precision="f32_fast", max_iterations=20, early_termination=True,
-                          fix_odd_check_sign=True, seed=5)
+                          fix_odd_check_sign=True, seed=5, kernel_flags=variant)
 
     def timed(eng, snr):
         best, res = 1e9, None
