@@ -85,7 +85,7 @@ struct GatherShape {
 template <class C, int T> struct TeamBase { static constexpr int value = TeamBase<C, T - 1>::value + C::template TeamSlots<T - 1>::value; };
 template <class C> struct TeamBase<C, 0> { static constexpr int value = 0; };
 
-// ---- CN phase: the rows of a team back to back, software pipelined (front of row g+1 next to back of row g) ----
+// ---- CN phase: the rows of a team back to back (the overlap of consecutive rows is left to ptxas, see cn_pipe) ----
 // A row's messages of the PREVIOUS pass: the edge buffer still holds them (the variable-node phase only reads it), and the
 // words are the thread's own -- one LDS.64 per edge at an immediate offset, no tensor-memory round trip, no store.
 template <int Z, class... S>
@@ -128,12 +128,16 @@ __device__ __forceinline__ void cn_pipe(const float2* __restrict__ post, float2*
 {
     using R = typename TeamRow<TEAM, GCUR>::type;
     using RN = typename TeamRow<TEAM, GNEXT>::type;
+    // Source order: the whole current row first, then the loads and the front half of the next one.  ptxas interleaves the
+    // two rows on its own, and how well depends on this order (one call, ms per launch: front of the next row before the
+    // back of the current one 16.75, back / front / emit 17.58, back / emit / front 16.40, this order 16.37; the front
+    // half split into its loads before and its exponentials after the current row 17.12 -- profiles/r2_tuning.md 5.10).
+    row_back2(R(), mcur, fcur);
+    row_emit<Z>(R(), mcur, ebuf, r, TBASE + EOFF, act);
     RowMsg<RN::D> mnext;
     row_prev<Z>(RN(), mnext, ebuf, r, TBASE + EOFF + R::D);
     RowFront2<RN::D> fnext;
     row_front2<Z, EARLY>(RN(), mnext, post, r, 0, fix_odd, act, ua, ub, fnext);
-    row_back2(R(), mcur, fcur);
-    row_emit<Z>(R(), mcur, ebuf, r, TBASE + EOFF, act);
     cn_pipe<Z, TEAM, TBASE, EOFF + R::D, EARLY>(post, ebuf, r, fix_odd, act, ua, ub, mnext, fnext, gn, rest...);
 }
 
