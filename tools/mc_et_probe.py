@@ -25,8 +25,8 @@ def main():
     import _native
     name = sys.argv[1] if len(sys.argv) > 1 else "wimax_2304_0.5"
     snrs = [float(a) for a in sys.argv[2:]] or [1.5, 2.0, 2.5, 3.0, 4.0]
-    # LDPC_ET_KERNEL=one_gather | pair_gather: force a kernel variant for the early-termination runs (A/B)
-    variant = {"one_gather": _native.FLAG_ONE_GATHER, "pair_gather": _native.FLAG_PAIR_GATHER}.get(os.environ.get("LDPC_ET_KERNEL", ""), 0)
+    # LDPC_ET_KERNEL=one_gather | pair_gather | one_frame: force a kernel variant for the early-termination runs (A/B)
+    variant = {"one_gather": _native.FLAG_ONE_GATHER, "pair_gather": _native.FLAG_PAIR_GATHER, "one_frame": _native.FLAG_ONE_FRAME}.get(os.environ.get("LDPC_ET_KERNEL", ""), 0)
     code = load_code(name)
     edd = EncoderDecoderData(h=code.sparse_matrix())
     frames = 262144
