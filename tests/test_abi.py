@@ -110,6 +110,30 @@ def test_nvrtc_specialises_an_unregistered_code_for_sm_100a(tmp_path, monkeypatc
     assert rc2 == 0 and size2 == size
 
 
+def test_nvrtc_module_carries_the_gather_kernel_for_narrow_rows(tmp_path, monkeypatch):
+    """A base matrix outside the registry whose rows have at most 8 edges (WiMAX r1/2 scaled to z = 28) gets the
+    two-frames-per-thread gather kernel in its NVRTC module as well (compiled with explicit 32-bit shared-window
+    addressing, csrc/qc_jit.cu); LDPC_JIT_GATHER=0 leaves it out.  Host only: NVRTC cross-compiles without a device."""
+    import json
+    reg = json.load(open(os.path.join(REPO, "ldpc-simulator_b200", "csrc", "qc_registry.json")))
+    base = np.array(reg[0]["shift"])
+    shift = np.where(base < 0, -1, base * 28 // 96)
+    monkeypatch.setenv("LDPC_JIT_CACHE", str(tmp_path))
+    monkeypatch.setenv("LDPC_JIT_GATHER", "0")
+    rc, _, small = _jit(28, shift, compile_it=True)
+    if rc != 0 and b"libnvrtc not found" in _native.lib().ldpc_last_error():
+        pytest.skip("no NVRTC on this machine")
+    assert rc == 0, _native.lib().ldpc_last_error()
+    monkeypatch.delenv("LDPC_JIT_GATHER")
+    rc, _, full = _jit(28, shift, compile_it=True)
+    assert rc == 0, _native.lib().ldpc_last_error()
+    assert full > small + 200_000                             # a third entry point of ~30 KB of SASS per team path + line info
+    cubins = sorted(os.path.getsize(tmp_path / f) for f in os.listdir(tmp_path) if f.endswith(".cubin"))
+    assert cubins == sorted([small, full])                    # two cache entries: the source text differs
+    blob = b"".join(open(tmp_path / f, "rb").read() for f in os.listdir(tmp_path) if f.endswith(".cubin"))
+    assert blob.count(b"ldpc_jit_gather") >= 1 and blob.count(b"ldpc_jit_fixed") >= 2
+
+
 def test_jit_rejects_what_the_kernel_cannot_run():
     lib = _native.lib()
     rc, _, _ = _jit(8, np.array([[0, 9]]))                    # shift >= z
