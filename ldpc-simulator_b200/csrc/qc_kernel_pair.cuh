@@ -177,23 +177,32 @@ __device__ __forceinline__ void row_front2(Row<S...>, RowMsg<sizeof...(S)>& m, c
     constexpr int SH[D > 0 ? D : 1] = {S::shift...};
     f.sgn_a = f.sgn_b = (fix_odd && (D & 1)) ? 0x80000000u : 0u;
     bool par_a = (D & 1) != 0, par_b = (D & 1) != 0;      // parity of the estimates, spa_decoder.py:188-195
+    // By kind of operation -- all loads, then all subtractions and sign products, then all exponentials -- rather than edge
+    // by edge: same instructions, but ptxas schedules this order 0.5-1.5 % faster (16.29 against 16.37-16.54 ms per launch,
+    // tools/r2_call54.sh; profiles/r2_tuning.md 5.10).
+    float2 Lv[D > 0 ? D : 1];
 #pragma unroll
     for (int c = 0; c < D; ++c) {
         int idx = r + SH[c];
         idx = (int)min((unsigned)idx, (unsigned)(idx - Z));      // (r + shift) mod z
 #ifdef LDPC_EXP_NOSMEM      // timing experiment (wrong results): no shared-memory traffic in the check-node phase
-        const float2 L = f2((float)(idx + c) * 0.01f, (float)(idx - c) * 0.02f);
+        Lv[c] = f2((float)(idx + c) * 0.01f, (float)(idx - c) * 0.02f);
 #else
-        const float2 L = act ? sh_ld2(sm, po + CB[c] + idx) : f2(1.f, 1.f);
+        Lv[c] = act ? sh_ld2(sm, po + CB[c] + idx) : f2(1.f, 1.f);
 #endif
-        const float2 mu = f2sub(L, m.v[c]);                      // variable->check messages, :260-268
-        if (EARLY) { par_a ^= (L.x < 0.f); par_b ^= (L.y < 0.f); }
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        const float2 mu = f2sub(Lv[c], m.v[c]);                  // variable->check messages, :260-268
+        if (EARLY) { par_a ^= (Lv[c].x < 0.f); par_b ^= (Lv[c].y < 0.f); }
         m.v[c] = mu;                                             // parked until row_back2 (signs)
         f.sgn_a ^= __float_as_uint(mu.x);
         f.sgn_b ^= __float_as_uint(mu.y);
-        f.x[c] = f2(ex2_approx(-fminf(fabsf(mu.x), kClipBits)),  // x = 2^-|m|, both clips of :133-146,167
-                    ex2_approx(-fminf(fabsf(mu.y), kClipBits)));
     }
+#pragma unroll
+    for (int c = 0; c < D; ++c)
+        f.x[c] = f2(ex2_approx(-fminf(fabsf(m.v[c].x), kClipBits)),      // x = 2^-|m|, both clips of :133-146,167
+                    ex2_approx(-fminf(fabsf(m.v[c].y), kClipBits)));
     if (EARLY) { unsat_a |= par_a; unsat_b |= par_b; }
 }
 
