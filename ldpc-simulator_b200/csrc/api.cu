@@ -26,6 +26,13 @@ int check_common(const ldpc_graph* g, int dtype, int64_t frames, int max_iter)
     // spa_decoder.py:104,244: with max_iterations <= 0 the reference loops until the syndrome
     // vanishes, possibly forever; refuse instead of hanging the GPU.
     if (max_iter < 1) { set_error("max_iter must be >= 1 (got %d)", max_iter); return LDPC_ERR_INVALID; }
+    // a handle's tables, run-time compiled modules and staging buffers live on the device it was created on
+    int dev = -1;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev != g->device) {
+        set_error("graph handle belongs to CUDA device %d, the calling thread's current device is %d "
+                  "(create one handle per device)", g->device, dev);
+        return LDPC_ERR_INVALID;
+    }
     return LDPC_OK;
 }
 
@@ -67,22 +74,40 @@ struct HostPipe {
     std::mutex mu;
     HostSlot slot[kSlots];
     bool init = false;
+    std::atomic<int> device{-1};         // bound to the device of its first caller (its streams and buffers live there)
     ReplayEntry replay[kReplaySlots];
     uint64_t replay_clock = 0;
 };
 constexpr int kPipes = 4;
 HostPipe g_pipes[kPipes];
 
-// Lock a pipeline: the first one that is free, else wait for the one this thread hashes to.
-HostPipe& acquire_pipe(std::unique_lock<std::mutex>& lk)
+// Lock a pipeline for a caller on `device`: the first free one that is unbound or bound to that device, else wait for one
+// of those; nullptr when every pipeline already belongs to another device.
+HostPipe* acquire_pipe(std::unique_lock<std::mutex>& lk, int device)
 {
-    for (auto& p : g_pipes) {
-        std::unique_lock<std::mutex> t(p.mu, std::try_to_lock);
-        if (t.owns_lock()) { lk = std::move(t); return p; }
+    HostPipe* fallback = nullptr;
+    const size_t start = std::hash<std::thread::id>()(std::this_thread::get_id()) % kPipes;
+    for (int pass = 0; pass < 2; ++pass) {                      // pipelines of this device first, unbound ones second
+        for (int i = 0; i < kPipes; ++i) {
+            HostPipe& p = g_pipes[(start * pass + i) % kPipes];
+            const int bound = p.device.load();
+            if (pass == 0 ? bound != device : bound != -1) continue;
+            if (!fallback) fallback = &p;
+            std::unique_lock<std::mutex> t(p.mu, std::try_to_lock);
+            if (!t.owns_lock()) continue;
+            const int now = p.device.load();                     // may have been bound while we looked
+            if (now != -1 && now != device) continue;
+            p.device.store(device);
+            lk = std::move(t);
+            return &p;
+        }
     }
-    HostPipe& p = g_pipes[std::hash<std::thread::id>()(std::this_thread::get_id()) % kPipes];
-    lk = std::unique_lock<std::mutex>(p.mu);
-    return p;
+    if (!fallback) return nullptr;
+    lk = std::unique_lock<std::mutex>(fallback->mu);
+    const int now = fallback->device.load();
+    if (now != -1 && now != device) { lk.unlock(); return nullptr; }
+    fallback->device.store(device);
+    return fallback;
 }
 
 int grow_dev(void** p, size_t* have, size_t need)
@@ -428,7 +453,9 @@ extern "C" int ldpc_decode_batch_host(const ldpc_graph* g, int dtype, int64_t fr
                             is_pinned(ok_host) && is_pinned(post_host) && is_pinned(norm_llr_host);
 
     std::unique_lock<std::mutex> lk;
-    HostPipe& pipe = acquire_pipe(lk);
+    HostPipe* pipe_p = acquire_pipe(lk, di.device);
+    if (!pipe_p) { set_error("all %d host staging pipelines are bound to other CUDA devices", kPipes); return LDPC_ERR_INVALID; }
+    HostPipe& pipe = *pipe_p;
     if (!pipe.init && (rc = init_pipe(pipe))) return rc;
     if (!resident && frames <= 32 && !(flags & LDPC_FLAG_NO_REPLAY) && !in_f16)
         return decode_host_replay(pipe, g, dtype, frames, max_iter, flags, llr_host, z_host, zbits_host, conv_iter_host, ok_host,

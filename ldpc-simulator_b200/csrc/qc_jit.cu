@@ -448,7 +448,8 @@ std::shared_ptr<JitKernel> build_kernel(const ldpc_graph* g)
 std::shared_ptr<JitKernel> get_kernel(const ldpc_graph* g)
 {
     std::lock_guard<std::mutex> lk(g_jit_mu);
-    const std::string key = cache_key(g->qc);
+    // a loaded module belongs to one device's context: the handle's device is part of the key
+    const std::string key = "dev" + std::to_string(g->device) + ":" + cache_key(g->qc);
     auto it = g_jit_cache.find(key);
     if (it != g_jit_cache.end()) return it->second;
     auto k = build_kernel(g);

@@ -361,12 +361,13 @@ int launch(const ldpc_graph* g, int64_t frames, int max_iter, unsigned flags, co
     auto kern = k_qc_resident<MB, DC, EARLY, THREADS, MINB>;
     const size_t smem = sizeof(float) * 3 * (size_t)g->n;
     if ((int)smem > di.max_smem_optin) { set_error("n=%d needs %zu bytes of shared memory", g->n, smem); return LDPC_ERR_UNSUPPORTED; }
-    static thread_local const void* configured = nullptr;
+    static thread_local const void* configured = nullptr;      // function attributes are per device: the key holds the ordinal
     static thread_local size_t configured_smem = 0;
-    if (configured != (const void*)kern || configured_smem < smem) {
+    static thread_local int configured_dev = -1;
+    if (configured != (const void*)kern || configured_smem < smem || configured_dev != di.device) {
         LDPC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LDPC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = (const void*)kern; configured_smem = smem;
+        configured = (const void*)kern; configured_smem = smem; configured_dev = di.device;
     }
     int per_sm = 0;
     LDPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));

@@ -808,3 +808,27 @@ def test_two_host_threads_decode_concurrently_on_separate_pipelines():
         for rep in range(4):
             for key in ("z", "ok", "conv_it", "post"):
                 assert np.array_equal(getattr(got[i][rep], key), getattr(want[i], key)), (i, rep, key)
+
+
+def test_a_handle_is_bound_to_its_device_and_a_second_device_gets_its_own_state():
+    """A graph handle, its run-time compiled modules and the host staging pipelines live on the device they were created
+    on (csrc/api.cu: check_common, acquire_pipe; csrc/qc_jit.cu: get_kernel).  A call from a thread whose current device is
+    another one is refused with LDPC_ERR_INVALID; a decoder built on the second device gives the same results."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    from _native import LdpcError
+    code = load_code("wimax_2304_0.5")
+    rng = np.random.default_rng(5)
+    llr = awgn_llr(rng, 3000, code.n, np.resize(np.array([1.5, 2.5]), 3000)).astype(np.float32)
+    dec0 = make_decoder(code, 10, "f32_fast", fix_odd_check_sign=True)
+    want = dec0.decode_batch(llr, want_posterior=True)
+    with torch.cuda.device(1):
+        with pytest.raises(LdpcError, match="belongs to CUDA device 0"):
+            dec0.decode_batch(llr)
+        dec1 = make_decoder(code, 10, "f32_fast", fix_odd_check_sign=True)
+        got = dec1.decode_batch(llr, want_posterior=True)
+    again = dec0.decode_batch(llr, want_posterior=True)
+    for key in ("z", "ok", "conv_it", "post"):
+        assert np.array_equal(getattr(got, key), getattr(want, key)), key
+        assert np.array_equal(getattr(again, key), getattr(want, key)), key
