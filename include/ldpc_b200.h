@@ -19,6 +19,11 @@
  *     tensors); the library owns only the opaque ldpc_graph handles.
  *   - a graph handle is immutable after creation and may be shared between
  *     streams and threads; a workspace belongs to one in-flight call.
+ *   - a graph handle lives on the CUDA device that was current when it was
+ *     created (its tables, run-time compiled modules and the staging
+ *     pipelines of ldpc_decode_batch_host).  Compute calls made while another
+ *     device is current fail with LDPC_ERR_INVALID; a process that drives
+ *     several GPUs creates one handle per device.
  *   - there is no CPU fallback: without a CUDA device every compute entry
  *     point fails with LDPC_ERR_CUDA.  The ldpc_host_* helpers are pure host
  *     integer code (graph analysis) and need no device.
